@@ -162,7 +162,7 @@ struct PoSim {
     double m_kp[ND], m_kd[ND], m_tq[ND], m_tv[ND], m_maximp[ND];
     int nobj; Obj obj[MAXOBJ];
     double table_x0, table_x1, table_y0, table_y1;
-    int last_contacts, last_iters;
+    int last_contacts, last_robot_contacts, last_iters;
     /* scratch of the last forward-dynamics pass (positions at the start of the sub-step) */
     double E[NL][9], r[NL][3], Rw[NL][9], pw[NL][3], S[NL][6];
     double IA[NL][36], U[NL][6], D[NL], u[NL], v[NL][6], c[NL][6], pA[NL][6];
@@ -489,13 +489,16 @@ void po_inverse_kinematics(const PoSim *s, int link, const double pos[3], const 
  *   robot collision boxes: hand (link 8), finger1 (link 9), finger2 (link 10), fixed in their link frames;
  *   objects: box (8 vertices) or z-cylinder (8 rim points, 4 per cap at 45 deg + k 90 deg);
  *   a contact = a vertex of body A against the signed-distance field of body B (plane / box / cylinder) with
- *   distance < CONTACT_MARGIN; pairs: object-table(+ground plane), robot box-table, robot box<->object (both
+ *   distance < CONTACT_MARGIN (4 mm: twice the largest per-sub-step approach, instead of Bullet's 2 cm breaking threshold,
+ *   to bound the row count); at most MAXC contacts (MAXRC on the robot) in collection order; pairs: object-table(+ground plane), robot box-table, robot box<->object (both
  *   directions), object<->object (both directions).
  * Rows follow btMultiBodyConstraintSolver::setupMultiBodyContactConstraint: speculative when distance > 0
  * (velocityError -= distance/dt), erp 0.2 when penetrating, friction = product of the two coefficients, two friction
  * directions from btPlaneSpace1 with the implicit cone clamp, finger links soft (stiffness 30000, damping 1000 ->
  * contact erp/cfm, App. B.3), no warm starting. */
-#define CONTACT_MARGIN 0.02
+#define CONTACT_MARGIN 0.004
+#define MAXC 24   /* contacts per env and sub-step; later candidates are dropped */
+#define MAXRC 16  /* of which contacts that involve a robot link */
 #define CONTACT_ERP 0.2
 #define LINEAR_SLOP 1e-5
 #define GROUND_Z (-0.4)
@@ -576,7 +579,9 @@ static void plane_space(const double *n, double *p, double *q) { /* btPlaneSpace
 }
 /* one contact: point P (world), normal n (world, pointing from B to A), distance; A/B are (link,obj) with -1/-1 = static */
 static void add_contact(PoSim *s, const double *gv, const double *P, const double *n, double dist, int linkA, int objA, int linkB, int objB, double mu, int soft) {
-    if (s->nrows + 3 > MAXROWS) return;
+    int on_robot = linkA >= 0 || linkB >= 0;
+    if (s->last_contacts >= MAXC || (on_robot && s->last_robot_contacts >= MAXRC)) return;
+    if (on_robot) s->last_robot_contacts++;
     double t1[3], t2[3]; plane_space(n, t1, t2);
     const double *dirs[3] = {n, t1, t2};
     int nrow = s->nrows;
@@ -686,7 +691,7 @@ static void substep(PoSim *s) {
     for (int o = 0; o < s->nobj; o++) { v3cpy(gv + ND + 6 * o, s->obj[o].lin); v3cpy(gv + ND + 6 * o + 3, s->obj[o].ang); }
 
     /* rows: joint limits (link order, lower then upper), motors, then contacts */
-    s->nrows = 0; s->last_contacts = 0;
+    s->nrows = 0; s->last_contacts = 0; s->last_robot_contacts = 0;
     for (int d = 0; d < ND; d++) for (int side = 0; side < 2; side++) {
         const LinkDef *L = &LINKS[DOF_LINK[d]]; Row *r = &s->rows[s->nrows++]; memset(r, 0, sizeof *r);
         double sg = side == 0 ? 1.0 : -1.0, pen = side == 0 ? s->q[d] - L->lo : L->hi - s->q[d];
@@ -847,4 +852,27 @@ void po_env_step(PoEnv *e, const float *action, float *obs, float *ag, float *dg
     env_obs(e, obs, ag, dg);
     po_is_success_f32(e->task, ag, dg, terminated, 1);
     po_compute_reward_f32(e->task, e->reward, ag, dg, reward, 1);
+}
+
+/* ------------------------------------------------------------------ CPU baseline driver (bench.py cpu_baseline / --impl reference)
+ * Random-action rollout of one env, reset on success or at the TimeLimit (test/envs_test.py:6-14 loop), xorshift actions. */
+static double rnd01(unsigned long long *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return (double)(*s >> 11) / 9007199254740992.0; }
+double po_bench_run(int task, int control, int n_steps, unsigned long long seed) {
+    PoEnv *e = po_env_create(task, control, PO_REWARD_SPARSE);
+    unsigned long long st = seed * 2654435761ULL + 88172645463325252ULL;
+    float obs[32], ag[6], dg[6], rew, act[8]; unsigned char term = 0; double acc = 0; int t = 0, na = po_env_action_dim(e), limit = task == PO_STACK ? 100 : 50;
+    for (int i = 0; i < n_steps; i++) {
+        if (i == 0 || term || t >= limit) {
+            double goal[6] = {0.3 * rnd01(&st) - 0.15, 0.3 * rnd01(&st) - 0.15, task == PO_REACH ? 0.3 * rnd01(&st) : 0.02, 0, 0, 0.06};
+            double op[6] = {0.3 * rnd01(&st) - 0.15, 0.3 * rnd01(&st) - 0.15, task == PO_SLIDE ? 0.03 : 0.02, 0.3 * rnd01(&st) - 0.15, 0.3 * rnd01(&st) - 0.15, 0.06};
+            if (task == PO_STACK) { goal[3] = goal[0]; goal[4] = goal[1]; }
+            if (task == PO_FLIP) { goal[0] = goal[1] = goal[2] = 0; goal[3] = 1; }
+            po_env_reset(e, goal, op, obs, ag, dg); t = 0;
+        }
+        for (int k = 0; k < na; k++) act[k] = (float)(2 * rnd01(&st) - 1);
+        po_env_step(e, act, obs, ag, dg, &rew, &term); t++;
+        acc += obs[0] + rew;
+    }
+    po_env_destroy(e);
+    return acc;
 }

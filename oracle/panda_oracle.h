@@ -74,6 +74,9 @@ void po_env_set_state(PoEnv *e, const double *q, const double *qd);
 void po_env_get_state(PoEnv *e, double *q, double *qd);
 void po_env_step(PoEnv *e, const float *action, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated);
 
+/* CPU baseline driver: random-action rollout of one env for n_steps env steps (reset on success / TimeLimit) */
+double po_bench_run(int task, int control, int n_steps, unsigned long long seed);
+
 /* ---- rewards (utils.py:4-30; tasks/ is_success / compute_reward) ---- */
 void po_compute_reward_f32(int task, int reward_type, const float *ag, const float *dg, float *out, long n);
 void po_is_success_f32(int task, const float *ag, const float *dg, unsigned char *out, long n);

@@ -1,0 +1,294 @@
+// panda_b200.cu -- C ABI of libpanda_b200.so (include/panda_b200.h): handle management, SoA state allocation, snapshots,
+// kernel dispatch, the host-buffer entry points and the HER reward kernels.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "panda_b200.h"
+#include "panda_kernels.cuh"
+#include "panda_model.h"
+#include "panda_scene.h"
+
+namespace pg {
+long long g_launches = 0;
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) { return fail(PG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+#define PG_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
+
+#define PG_DECL(T, K)                                                                                        \
+    extern template void launch_step<T, K>(const EnvDev<T>&, int, const StepIO&, cudaStream_t);              \
+    extern template void launch_reset<T, K>(const EnvDev<T>&, const ResetIO&, cudaStream_t);                 \
+    extern template void launch_get_state<T, K>(const EnvDev<T>&, double*, cudaStream_t);                    \
+    extern template void launch_set_state<T, K>(const EnvDev<T>&, const double*, const unsigned char*, cudaStream_t);
+PG_DECL(float, 0) PG_DECL(float, 1) PG_DECL(float, 2) PG_DECL(float, 3) PG_DECL(float, 4) PG_DECL(float, 5)
+PG_DECL(double, 0) PG_DECL(double, 1) PG_DECL(double, 2) PG_DECL(double, 3) PG_DECL(double, 4) PG_DECL(double, 5)
+
+template <typename T> struct Dispatch {
+    static void step(int task, const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st) {
+        switch (task) {
+        case 0: launch_step<T, 0>(E, ctrl, io, st); break; case 1: launch_step<T, 1>(E, ctrl, io, st); break;
+        case 2: launch_step<T, 2>(E, ctrl, io, st); break; case 3: launch_step<T, 3>(E, ctrl, io, st); break;
+        case 4: launch_step<T, 4>(E, ctrl, io, st); break; default: launch_step<T, 5>(E, ctrl, io, st); break;
+        }
+    }
+    static void reset(int task, const EnvDev<T>& E, const ResetIO& io, cudaStream_t st) {
+        switch (task) {
+        case 0: launch_reset<T, 0>(E, io, st); break; case 1: launch_reset<T, 1>(E, io, st); break;
+        case 2: launch_reset<T, 2>(E, io, st); break; case 3: launch_reset<T, 3>(E, io, st); break;
+        case 4: launch_reset<T, 4>(E, io, st); break; default: launch_reset<T, 5>(E, io, st); break;
+        }
+    }
+    static void get_state(int task, const EnvDev<T>& E, double* out, cudaStream_t st) {
+        switch (task) {
+        case 0: launch_get_state<T, 0>(E, out, st); break; case 1: launch_get_state<T, 1>(E, out, st); break;
+        case 2: launch_get_state<T, 2>(E, out, st); break; case 3: launch_get_state<T, 3>(E, out, st); break;
+        case 4: launch_get_state<T, 4>(E, out, st); break; default: launch_get_state<T, 5>(E, out, st); break;
+        }
+    }
+    static void set_state(int task, const EnvDev<T>& E, const double* in, const unsigned char* mask, cudaStream_t st) {
+        switch (task) {
+        case 0: launch_set_state<T, 0>(E, in, mask, st); break; case 1: launch_set_state<T, 1>(E, in, mask, st); break;
+        case 2: launch_set_state<T, 2>(E, in, mask, st); break; case 3: launch_set_state<T, 3>(E, in, mask, st); break;
+        case 4: launch_set_state<T, 4>(E, in, mask, st); break; default: launch_set_state<T, 5>(E, in, mask, st); break;
+        }
+    }
+};
+}  // namespace pg
+
+using namespace pg;
+
+struct pg_env {
+    int task, ctrl, reward, n, device, precision;
+    int obs_dim, goal_dim, act_dim, max_steps, state_dim, nobj;
+    void* blob = nullptr; size_t blob_bytes = 0;      // one allocation: q, qd, obj, goal, steps, episode, ret, stats
+    EnvDev<float> Ef; EnvDev<double> Ed;
+    std::map<int, void*> snaps; int next_snap = 0;
+    // host-buffer path: pinned staging + device I/O buffers + private stream
+    cudaStream_t hstream = nullptr;
+    float *h_act = nullptr, *h_out = nullptr; float* d_act = nullptr; float* d_out = nullptr; size_t out_floats = 0; size_t out_bytes = 0;
+};
+
+template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsigned long long seed, long long id0) {
+    const size_t n = (size_t)e->n;
+    E.n = e->n; E.reward_type = e->reward; E.id0 = id0; E.seed = seed;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 255) & ~(size_t)255; return p; };
+    E.stats = (double*)take(4 * sizeof(double));
+    E.q = (T*)take(9 * n * sizeof(T)); E.qd = (T*)take(9 * n * sizeof(T));
+    E.obj = (T*)take((size_t)(e->nobj > 0 ? e->nobj : 1) * 13 * n * sizeof(T));
+    E.goal = (T*)take(6 * n * sizeof(T));
+    E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
+    e->blob_bytes = off;
+}
+
+template <typename E, bool WANT_REWARD> static void launch_reward(int task, const E* ag, const E* dg, float* reward, unsigned char* success, long long m, int reward_type, cudaStream_t st) {
+    long long blocks = (m + BLOCK - 1) / BLOCK;
+    int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);   // persistent-style grid: a multiple of the SM count, rows strided
+    switch (task) {
+    case 4: reward_kernel<E, 4, WANT_REWARD><<<grid, BLOCK, 0, st>>>(ag, dg, reward, success, m, reward_type); break;
+    case 5: reward_kernel<E, 5, WANT_REWARD><<<grid, BLOCK, 0, st>>>(ag, dg, reward, success, m, reward_type); break;
+    default: reward_kernel<E, 0, WANT_REWARD><<<grid, BLOCK, 0, st>>>(ag, dg, reward, success, m, reward_type); break;   // all 3-D position goals share thr 0.05
+    }
+    g_launches++;
+}
+
+extern "C" {
+
+const char* pg_last_error(void) { return g_err.c_str(); }
+long long pg_kernel_launches(void) { return g_launches; }
+
+int pg_create(int task, int control_type, int reward_type, int num_envs, int device, unsigned long long seed, long long env_id_offset,
+              int precision, pg_env** out) {
+    if (!out) return fail(PG_ERR_ARG, "pg_create: out is NULL");
+    if (task < 0 || task > 5 || control_type < 0 || control_type > 1 || reward_type < 0 || reward_type > 1 || num_envs <= 0 || precision < 0 || precision > 1)
+        return fail(PG_ERR_ARG, "pg_create: bad task / control_type / reward_type / num_envs / precision");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return fail(PG_ERR_CUDA, std::string("pg_create: no CUDA device (") + cudaGetErrorString(ce) + "); this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(PG_ERR_ARG, "pg_create: bad device index");
+    PG_CUDA(cudaSetDevice(device));
+    pg_env* e = new pg_env();
+    e->task = task; e->ctrl = control_type; e->reward = reward_type; e->n = num_envs; e->device = device; e->precision = precision;
+    e->nobj = task_nobj(task); e->obs_dim = task_obs_dim(task); e->goal_dim = task_goal_dim(task); e->act_dim = task_act_dim(task, control_type);
+    e->max_steps = task_max_steps(task); e->state_dim = 18 + 13 * e->nobj + e->goal_dim + 1;
+    const double base[3] = {-0.6, 0.0, 0.0};   // panda_tasks.py:26,43,60,77,94,111
+    if (precision == PG_F32) { bind(e->Ef, e, nullptr, seed, env_id_offset); } else { bind(e->Ed, e, nullptr, seed, env_id_offset); }
+    cudaError_t err = cudaMalloc(&e->blob, e->blob_bytes);
+    if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaMalloc(state)"); }
+    cudaMemset(e->blob, 0, e->blob_bytes);
+    if (precision == PG_F32) { bind(e->Ef, e, (char*)e->blob, seed, env_id_offset); e->Ef.M = make_model<float>(base); e->Ef.S = make_scene<float>(task); }
+    else { bind(e->Ed, e, (char*)e->blob, seed, env_id_offset); e->Ed.M = make_model<double>(base); e->Ed.S = make_scene<double>(task); }
+    *out = e;
+    int rc = pg_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc != PG_OK) { pg_destroy(e); *out = nullptr; return rc; }
+    PG_CUDA(cudaDeviceSynchronize());
+    return PG_OK;
+}
+
+int pg_destroy(pg_env* e) {
+    if (!e) return PG_OK;
+    cudaSetDevice(e->device);
+    for (auto& kv : e->snaps) cudaFree(kv.second);
+    if (e->h_act) cudaFreeHost(e->h_act);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->d_act) cudaFree(e->d_act);
+    if (e->d_out) cudaFree(e->d_out);
+    if (e->hstream) cudaStreamDestroy(e->hstream);
+    cudaFree(e->blob);
+    delete e;
+    return PG_OK;
+}
+
+int pg_dims(const pg_env* e, int* obs_dim, int* goal_dim, int* action_dim, int* max_episode_steps, int* state_dim) {
+    if (!e) return fail(PG_ERR_ARG, "pg_dims: NULL handle");
+    if (obs_dim) *obs_dim = e->obs_dim; if (goal_dim) *goal_dim = e->goal_dim; if (action_dim) *action_dim = e->act_dim;
+    if (max_episode_steps) *max_episode_steps = e->max_steps; if (state_dim) *state_dim = e->state_dim;
+    return PG_OK;
+}
+
+int pg_reset(pg_env* e, const unsigned char* mask, const double* goal_override, const double* object_override, float* obs, float* ag, float* dg, void* stream) {
+    if (!e) return fail(PG_ERR_ARG, "pg_reset: NULL handle");
+    PG_CUDA(cudaSetDevice(e->device));
+    ResetIO io{mask, goal_override, object_override, obs, ag, dg};
+    if (e->precision == PG_F32) Dispatch<float>::reset(e->task, e->Ef, io, (cudaStream_t)stream); else Dispatch<double>::reset(e->task, e->Ed, io, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+int pg_step(pg_env* e, const float* actions, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated, unsigned char* truncated,
+            int auto_reset, void* stream) {
+    if (!e || !actions) return fail(PG_ERR_ARG, "pg_step: NULL handle or actions");
+    PG_CUDA(cudaSetDevice(e->device));
+    StepIO io{actions, obs, ag, dg, reward, terminated, truncated, auto_reset};
+    if (e->precision == PG_F32) Dispatch<float>::step(e->task, e->Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, e->Ed, e->ctrl, io, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+
+static int ensure_host_path(pg_env* e) {
+    if (e->hstream) return PG_OK;
+    const size_t n = (size_t)e->n;
+    // one pinned + one device output slab: obs | ag | dg | reward | terminated | truncated (flags padded to floats)
+    e->out_floats = n * (size_t)(e->obs_dim + 2 * e->goal_dim + 1) + (2 * n + 3) / 4 + 4;
+    e->out_bytes = e->out_floats * sizeof(float);
+    PG_CUDA(cudaStreamCreate(&e->hstream));
+    PG_CUDA(cudaMallocHost(&e->h_act, n * e->act_dim * sizeof(float)));
+    PG_CUDA(cudaMallocHost(&e->h_out, e->out_bytes));
+    PG_CUDA(cudaMalloc(&e->d_act, n * e->act_dim * sizeof(float)));
+    PG_CUDA(cudaMalloc(&e->d_out, e->out_bytes));
+    return PG_OK;
+}
+
+int pg_step_host(pg_env* e, const float* actions, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated, unsigned char* truncated, int auto_reset) {
+    if (!e || !actions) return fail(PG_ERR_ARG, "pg_step_host: NULL handle or actions");
+    PG_CUDA(cudaSetDevice(e->device));
+    int rc = ensure_host_path(e); if (rc != PG_OK) return rc;
+    const size_t n = (size_t)e->n, O = e->obs_dim, G = e->goal_dim;
+    memcpy(e->h_act, actions, n * e->act_dim * sizeof(float));
+    PG_CUDA(cudaMemcpyAsync(e->d_act, e->h_act, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, e->hstream));
+    float* d_obs = e->d_out; float* d_ag = d_obs + n * O; float* d_dg = d_ag + n * G; float* d_rew = d_dg + n * G;
+    unsigned char* d_term = (unsigned char*)(d_rew + n); unsigned char* d_trunc = d_term + n;
+    rc = pg_step(e, e->d_act, d_obs, d_ag, d_dg, d_rew, d_term, d_trunc, auto_reset, e->hstream); if (rc != PG_OK) return rc;
+    PG_CUDA(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->hstream));
+    PG_CUDA(cudaStreamSynchronize(e->hstream));
+    const float* h = e->h_out;
+    if (obs) memcpy(obs, h, n * O * sizeof(float));
+    if (ag) memcpy(ag, h + n * O, n * G * sizeof(float));
+    if (dg) memcpy(dg, h + n * O + n * G, n * G * sizeof(float));
+    if (reward) memcpy(reward, h + n * O + 2 * n * G, n * sizeof(float));
+    const unsigned char* hf = (const unsigned char*)(h + n * O + 2 * n * G + n);
+    if (terminated) memcpy(terminated, hf, n);
+    if (truncated) memcpy(truncated, hf + n, n);
+    return PG_OK;
+}
+
+int pg_compute_reward(int task, int reward_type, const void* ag, const void* dg, float* reward, long long m, int dtype, void* stream) {
+    if (task < 0 || task > 5 || !ag || !dg || !reward || m < 0) return fail(PG_ERR_ARG, "pg_compute_reward: bad argument");
+    if (m == 0) return PG_OK;
+    if (dtype == PG_F32) launch_reward<float, true>(task, (const float*)ag, (const float*)dg, reward, nullptr, m, reward_type, (cudaStream_t)stream);
+    else launch_reward<double, true>(task, (const double*)ag, (const double*)dg, reward, nullptr, m, reward_type, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_is_success(int task, const void* ag, const void* dg, unsigned char* success, long long m, int dtype, void* stream) {
+    if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success: bad argument");
+    if (m == 0) return PG_OK;
+    if (dtype == PG_F32) launch_reward<float, false>(task, (const float*)ag, (const float*)dg, nullptr, success, m, 0, (cudaStream_t)stream);
+    else launch_reward<double, false>(task, (const double*)ag, (const double*)dg, nullptr, success, m, 0, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_compute_reward_host(int task, int reward_type, const void* ag, const void* dg, float* reward, long long m, int dtype, int device) {
+    if (task < 0 || task > 5 || !ag || !dg || !reward || m < 0) return fail(PG_ERR_ARG, "pg_compute_reward_host: bad argument");
+    if (m == 0) return PG_OK;
+    PG_CUDA(cudaSetDevice(device));
+    const size_t es = dtype == PG_F32 ? 4 : 8, bytes = (size_t)m * task_goal_dim(task) * es;
+    void *da = nullptr, *db = nullptr; float* dr = nullptr;
+    PG_CUDA(cudaMalloc(&da, bytes)); PG_CUDA(cudaMalloc(&db, bytes)); PG_CUDA(cudaMalloc(&dr, (size_t)m * 4));
+    PG_CUDA(cudaMemcpy(da, ag, bytes, cudaMemcpyHostToDevice)); PG_CUDA(cudaMemcpy(db, dg, bytes, cudaMemcpyHostToDevice));
+    int rc = pg_compute_reward(task, reward_type, da, db, dr, m, dtype, nullptr);
+    if (rc == PG_OK) { cudaError_t ce = cudaMemcpy(reward, dr, (size_t)m * 4, cudaMemcpyDeviceToHost); if (ce != cudaSuccess) rc = cuda_fail(ce, "cudaMemcpy(reward)"); }
+    cudaFree(da); cudaFree(db); cudaFree(dr);
+    return rc;
+}
+
+int pg_save_state(pg_env* e, int* state_id) {
+    if (!e || !state_id) return fail(PG_ERR_ARG, "pg_save_state: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    void* p = nullptr;
+    PG_CUDA(cudaMalloc(&p, e->blob_bytes));
+    PG_CUDA(cudaMemcpy(p, e->blob, e->blob_bytes, cudaMemcpyDeviceToDevice));
+    *state_id = e->next_snap++; e->snaps[*state_id] = p;
+    return PG_OK;
+}
+int pg_restore_state(pg_env* e, int state_id) {
+    if (!e) return fail(PG_ERR_ARG, "pg_restore_state: NULL handle");
+    auto it = e->snaps.find(state_id);
+    if (it == e->snaps.end()) return fail(PG_ERR_STATE, "pg_restore_state: unknown state id " + std::to_string(state_id));
+    PG_CUDA(cudaSetDevice(e->device));
+    PG_CUDA(cudaMemcpy(e->blob, it->second, e->blob_bytes, cudaMemcpyDeviceToDevice));
+    return PG_OK;
+}
+int pg_remove_state(pg_env* e, int state_id) {
+    if (!e) return fail(PG_ERR_ARG, "pg_remove_state: NULL handle");
+    auto it = e->snaps.find(state_id);
+    if (it == e->snaps.end()) return fail(PG_ERR_STATE, "pg_remove_state: unknown state id " + std::to_string(state_id));
+    cudaFree(it->second); e->snaps.erase(it);
+    return PG_OK;
+}
+
+int pg_get_state(pg_env* e, double* state, void* stream) {
+    if (!e || !state) return fail(PG_ERR_ARG, "pg_get_state: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    if (e->precision == PG_F32) Dispatch<float>::get_state(e->task, e->Ef, state, (cudaStream_t)stream); else Dispatch<double>::get_state(e->task, e->Ed, state, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_set_state(pg_env* e, const double* state, const unsigned char* mask, void* stream) {
+    if (!e || !state) return fail(PG_ERR_ARG, "pg_set_state: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    if (e->precision == PG_F32) Dispatch<float>::set_state(e->task, e->Ef, state, mask, (cudaStream_t)stream); else Dispatch<double>::set_state(e->task, e->Ed, state, mask, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_inverse_kinematics(pg_env* e, const double* position, const double* orientation, double* joint_angles, void* stream) {
+    if (!e || !position || !orientation || !joint_angles) return fail(PG_ERR_ARG, "pg_inverse_kinematics: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    const int grid = (e->n + BLOCK - 1) / BLOCK;
+    if (e->precision == PG_F32) ik_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(e->Ef, position, orientation, joint_angles);
+    else ik_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(e->Ed, position, orientation, joint_angles);
+    g_launches++;
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_stats(pg_env* e, double out[4]) {
+    if (!e || !out) return fail(PG_ERR_ARG, "pg_stats: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    PG_CUDA(cudaMemcpy(out, e->precision == PG_F32 ? e->Ef.stats : e->Ed.stats, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    return PG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// panda_env.cuh -- one environment step: action -> motor targets -> 20 sub-steps -> observation / goals / reward / success.
+//
+// Mirrors reference panda_gym/envs/core.py:280-289 (RobotTaskEnv.step), :229-238 (_get_obs),
+// panda_gym/envs/robots/panda.py:52-119 (set_action, get_obs), the per-task get_obs / get_achieved_goal /
+// is_success / compute_reward of panda_gym/envs/tasks/<task>.py and panda_gym/utils.py:4-30.
+#pragma once
+#include "panda_contact.cuh"
+
+namespace pg {
+
+enum { TASK_REACH = 0, TASK_PUSH = 1, TASK_SLIDE = 2, TASK_PICK_AND_PLACE = 3, TASK_STACK = 4, TASK_FLIP = 5 };
+enum { CTRL_EE = 0, CTRL_JOINTS = 1 };
+enum { REWARD_SPARSE = 0, REWARD_DENSE = 1 };
+
+PG_HD constexpr int task_nobj(int task) { return task == TASK_REACH ? 0 : (task == TASK_STACK ? 2 : 1); }
+PG_HD constexpr bool task_block_gripper(int task) { return task == TASK_REACH || task == TASK_PUSH || task == TASK_SLIDE; }   // panda_tasks.py:60,77,94
+PG_HD constexpr int task_goal_dim(int task) { return task == TASK_STACK ? 6 : (task == TASK_FLIP ? 4 : 3); }
+PG_HD constexpr int task_obs_dim(int task) { return (task_block_gripper(task) ? 6 : 7) + (task == TASK_REACH ? 0 : (task == TASK_STACK ? 24 : (task == TASK_FLIP ? 13 : 12))); }
+PG_HD constexpr int task_act_dim(int task, int ctrl) { return (ctrl == CTRL_EE ? 3 : 7) + (task_block_gripper(task) ? 0 : 1); }
+PG_HD constexpr int task_max_steps(int task) { return task == TASK_STACK ? 100 : 50; }   // panda_gym/__init__.py:18,46
+
+// float32 arithmetic exactly as numpy evaluates it: no fused multiply-add
+#ifdef __CUDA_ARCH__
+PG_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
+PG_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+PG_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+PG_HD float f_sqrt(float a) { return __fsqrt_rn(a); }
+PG_HD double d_sub(double a, double b) { return __dsub_rn(a, b); }
+PG_HD double d_add(double a, double b) { return __dadd_rn(a, b); }
+PG_HD double d_mul(double a, double b) { return __dmul_rn(a, b); }
+PG_HD double d_sqrt(double a) { return __dsqrt_rn(a); }
+#else
+PG_HD float f_sub(float a, float b) { return a - b; }
+PG_HD float f_add(float a, float b) { return a + b; }
+PG_HD float f_mul(float a, float b) { return a * b; }
+PG_HD float f_sqrt(float a) { return sqrtf(a); }
+PG_HD double d_sub(double a, double b) { return a - b; }
+PG_HD double d_add(double a, double b) { return a + b; }
+PG_HD double d_mul(double a, double b) { return a * b; }
+PG_HD double d_sqrt(double a) { return sqrt(a); }
+#endif
+PG_HD float threshold_f32(int task) { return task == TASK_STACK ? 0.1f : (task == TASK_FLIP ? 0.2f : 0.05f); }
+PG_HD double threshold_f64(int task) { return task == TASK_STACK ? 0.1 : (task == TASK_FLIP ? 0.2 : 0.05); }
+// utils.distance (np.linalg.norm(a-b, axis=-1): squares summed left to right) / utils.angle_distance row-wise (1 - <a,b>^2)
+PG_HD float goal_distance(int task, const float* a, const float* b) {
+    if (task == TASK_FLIP) {
+        float s = f_add(f_add(f_mul(a[0], b[0]), f_mul(a[1], b[1])), f_add(f_mul(a[2], b[2]), f_mul(a[3], b[3])));
+        return f_sub(1.0f, f_mul(s, s));
+    }
+    const int g = task_goal_dim(task);
+    float d0 = f_sub(a[0], b[0]), acc = f_mul(d0, d0);
+    for (int k = 1; k < g; k++) { float d = f_sub(a[k], b[k]); acc = f_add(acc, f_mul(d, d)); }
+    return f_sqrt(acc);
+}
+PG_HD double goal_distance(int task, const double* a, const double* b) {
+    if (task == TASK_FLIP) {
+        double s = d_add(d_add(d_mul(a[0], b[0]), d_mul(a[1], b[1])), d_add(d_mul(a[2], b[2]), d_mul(a[3], b[3])));
+        return d_sub(1.0, d_mul(s, s));
+    }
+    const int g = task_goal_dim(task);
+    double d0 = d_sub(a[0], b[0]), acc = d_mul(d0, d0);
+    for (int k = 1; k < g; k++) { double d = d_sub(a[k], b[k]); acc = d_add(acc, d_mul(d, d)); }
+    return d_sqrt(acc);
+}
+// sparse: -(d > thr).astype(float32) -> -1.0 or -0.0;  dense: -d.astype(float32)
+PG_HD float reward_from_distance(int reward_type, float d, float thr) { return reward_type == REWARD_SPARSE ? -(d > thr ? 1.0f : 0.0f) : -d; }
+PG_HD float reward_from_distance(int reward_type, double d, double thr) { return reward_type == REWARD_SPARSE ? -(d > thr ? 1.0f : 0.0f) : -(float)d; }
+
+// pybullet getEulerFromQuaternion
+template <typename T> PG_HD void euler_from_quat(T x, T y, T z, T w, T* e) {
+    T sarg = T(-2) * (x * z - w * y);
+    const T hp = Consts<T>::pi / 2;
+    if (sarg <= T(-0.99999)) { e[0] = T(0); e[1] = -hp; e[2] = 2 * atan2(x, -y); }
+    else if (sarg >= T(0.99999)) { e[0] = T(0); e[1] = hp; e[2] = 2 * atan2(-x, y); }
+    else {
+        e[0] = atan2(2 * (y * z + w * x), w * w - x * x - y * y + z * z);
+        e[1] = asin(sarg);
+        e[2] = atan2(2 * (x * y + w * z), w * w + x * x - y * y - z * z);
+    }
+}
+
+// _get_obs: robot obs (ee pos, ee vel[, finger width]) ++ task obs; achieved goal; desired goal
+template <typename T, int TASK>
+PG_HD void env_observe(const Model<T>& M, const T* q, const T* qd, const T* qc, const Obj<T>* ob, const T* goal, float* obs, float* ag, float* dg) {
+    constexpr int NOBJ = task_nobj(TASK);
+    V3<T> p, v; ee_observe(M, q, qd, qc, p, v);
+    int n = 0;
+    obs[n++] = (float)p.x; obs[n++] = (float)p.y; obs[n++] = (float)p.z;
+    obs[n++] = (float)v.x; obs[n++] = (float)v.y; obs[n++] = (float)v.z;
+    if (!task_block_gripper(TASK)) obs[n++] = (float)(q[7] + q[8]);
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        obs[n++] = (float)ob[o].pos.x; obs[n++] = (float)ob[o].pos.y; obs[n++] = (float)ob[o].pos.z;
+        if (TASK == TASK_FLIP) { obs[n++] = (float)ob[o].qx; obs[n++] = (float)ob[o].qy; obs[n++] = (float)ob[o].qz; obs[n++] = (float)ob[o].qw; }
+        else { T e[3]; euler_from_quat(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw, e); obs[n++] = (float)e[0]; obs[n++] = (float)e[1]; obs[n++] = (float)e[2]; }
+        obs[n++] = (float)ob[o].lin.x; obs[n++] = (float)ob[o].lin.y; obs[n++] = (float)ob[o].lin.z;
+        obs[n++] = (float)ob[o].ang.x; obs[n++] = (float)ob[o].ang.y; obs[n++] = (float)ob[o].ang.z;
+    }
+    if (TASK == TASK_REACH) { ag[0] = (float)p.x; ag[1] = (float)p.y; ag[2] = (float)p.z; }
+    else if (TASK == TASK_FLIP) { ag[0] = (float)ob[0].qx; ag[1] = (float)ob[0].qy; ag[2] = (float)ob[0].qz; ag[3] = (float)ob[0].qw; }
+    else {
+#pragma unroll
+        for (int o = 0; o < NOBJ; o++) { ag[3 * o] = (float)ob[o].pos.x; ag[3 * o + 1] = (float)ob[o].pos.y; ag[3 * o + 2] = (float)ob[o].pos.z; }
+    }
+#pragma unroll
+    for (int k = 0; k < task_goal_dim(TASK); k++) dg[k] = (float)goal[k];
+}
+
+// Panda.set_action: clip, arm target from the ee displacement (IK) or the joint deltas, finger target
+template <typename T, int TASK, int CTRL>
+PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const float* action, T* target) {
+    constexpr int NA = task_act_dim(TASK, CTRL);
+    T a[NA];
+#pragma unroll
+    for (int k = 0; k < NA; k++) { T v = (T)action[k]; a[k] = v < T(-1) ? T(-1) : (v > T(1) ? T(1) : v); }
+    if (CTRL == CTRL_EE) {
+        // the EE position the reference reads is the cached one, FK(q - qd dt)
+        T qc[ND];
+#pragma unroll
+        for (int d = 0; d < ND; d++) qc[d] = q[d] - qd[d] * Consts<T>::dt;
+        Frame<T> F[7]; fk_arm(M, qc, F);
+        V3<T> p = F[6].p + F[6].Z * M.eez;
+        p.x += a[0] * T(0.05); p.y += a[1] * T(0.05); p.z += a[2] * T(0.05);
+        if (p.z < T(0)) p.z = T(0);
+        const T tq[4] = {T(1), T(0), T(0), T(0)};
+        ik_ee(M, q, p, tq, target);
+    } else {
+#pragma unroll
+        for (int d = 0; d < 7; d++) target[d] = q[d] + a[d] * T(0.05);
+    }
+    T w = task_block_gripper(TASK) ? T(0) : (q[7] + q[8]) + a[NA - 1] * T(0.2);
+    target[7] = w / 2; target[8] = w / 2;
+}
+
+// RobotTaskEnv.step for one environment.  q/qd/ob are updated in place.
+template <typename T, int TASK, int CTRL>
+PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action,
+                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C) {
+    constexpr int NOBJ = task_nobj(TASK);
+    T target[ND], qc[ND];
+    env_set_action<T, TASK, CTRL>(M, q, qd, action, target);
+    for (int s = 0; s < 20; s++) {
+        if (s == 19) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
+        }
+        env_substep<T, NOBJ>(M, S, q, qd, target, ob, C);
+    }
+    env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
+    float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);
+    success = d < thr;
+    reward = reward_from_distance(reward_type, d, thr);
+}
+
+}  // namespace pg

@@ -1,0 +1,319 @@
+// panda_kernels.cuh -- the CUDA kernels: one thread per environment, structure-of-arrays state in HBM, I/O rows staged
+// through shared memory so that every global access is a coalesced (and where aligned, 16-byte) transaction, the whole
+// env step (controller, 20 sub-steps, observation, reward, optional auto-reset) fused into one launch so the state is read
+// once and written once per step.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "panda_env.cuh"
+
+namespace pg {
+
+constexpr int BLOCK = 128;
+
+template <typename T> struct EnvDev {
+    int n;                       // environments on this device
+    int reward_type;
+    long long id0;               // global index of env 0 (RNG key)
+    unsigned long long seed;
+    T* q;                        // [9][n]
+    T* qd;                       // [9][n]
+    T* obj;                      // [nobj][13][n]  pos3 quat4 lin3 ang3
+    T* goal;                     // [6][n]
+    int* steps;                  // [n] steps since reset (TimeLimit)
+    unsigned* episode;           // [n] episodes started (RNG counter)
+    float* ret;                  // [n] running episode return
+    double* stats;               // [4] episodes, successes, return sum, length sum
+    Model<T> M;
+    Scene<T> S;
+};
+struct StepIO {
+    const float* actions; float* obs; float* ag; float* dg; float* reward; unsigned char* terminated; unsigned char* truncated;
+    int auto_reset;
+};
+struct ResetIO {
+    const unsigned char* mask; const double* goal_override; const double* object_override; float* obs; float* ag; float* dg;
+};
+
+// ---------------------------------------------------------------------------------------------- Philox4x32-10
+struct Philox {
+    uint32_t c[4], k[2], out[4]; int have;
+    __device__ Philox(unsigned long long seed, unsigned long long env, uint32_t episode) {
+        k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32); c[0] = (uint32_t)env; c[1] = (uint32_t)(env >> 32); c[2] = episode; c[3] = 0; have = 0;
+    }
+    __device__ void round4() {
+        uint32_t a[4] = {c[0], c[1], c[2], c[3]}, key[2] = {k[0], k[1]};
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, a[0]), lo0 = 0xD2511F53u * a[0], hi1 = __umulhi(0xCD9E8D57u, a[2]), lo1 = 0xCD9E8D57u * a[2];
+            uint32_t n0 = hi1 ^ a[1] ^ key[0], n1 = lo1, n2 = hi0 ^ a[3] ^ key[1], n3 = lo0;
+            a[0] = n0; a[1] = n1; a[2] = n2; a[3] = n3; key[0] += 0x9E3779B9u; key[1] += 0xBB67AE85u;
+        }
+        out[0] = a[0]; out[1] = a[1]; out[2] = a[2]; out[3] = a[3]; c[3]++; have = 4;
+    }
+    __device__ uint32_t next() { if (have == 0) round4(); return out[4 - have--]; }
+    __device__ double uniform() { uint32_t a = next() >> 5, b = next() >> 6; return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0); }   // 53 bits, [0,1)
+    __device__ double uniform(double lo, double hi) { return lo + (hi - lo) * uniform(); }
+    __device__ double normal() { double u1 = 1.0 - uniform(), u2 = uniform(); return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); }
+};
+
+// ---------------------------------------------------------------------------------------------- I/O tiles
+// rows [row0, row0 + BLOCK) of a row-major [n, W] array <-> per-thread registers, through shared memory
+template <int W, typename E> __device__ __forceinline__ void tile_load(E* s, const E* g, long long row0, int n, E* reg) {
+    const long long base = row0 * W;
+    const int cnt = (int)min((long long)BLOCK, (long long)n - row0) * W;
+    if (sizeof(E) == 4 && ((uintptr_t)(g + base) & 15) == 0) {
+        const int c4 = cnt >> 2;
+        for (int i = threadIdx.x; i < c4; i += BLOCK) reinterpret_cast<float4*>(s)[i] = __ldg(reinterpret_cast<const float4*>(g + base) + i);
+        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += BLOCK) s[i] = g[base + i];
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += BLOCK) s[i] = g[base + i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x * W < cnt) {
+#pragma unroll
+        for (int k = 0; k < W; k++) reg[k] = s[threadIdx.x * W + k];
+    }
+    __syncthreads();
+}
+// `write` is per-thread: rows whose thread passes write=false keep their previous contents
+template <int W, typename E> __device__ __forceinline__ void tile_store(E* s, E* g, long long row0, int n, const E* reg, bool all_write, bool write) {
+    if (g == nullptr) return;
+    const long long base = row0 * W;
+    const int cnt = (int)min((long long)BLOCK, (long long)n - row0) * W;
+    if (!all_write) {   // masked rows: each thread writes its own row directly
+        if (write && (int)threadIdx.x * W < cnt) {
+#pragma unroll
+            for (int k = 0; k < W; k++) g[base + threadIdx.x * W + k] = reg[k];
+        }
+        return;
+    }
+    if ((int)threadIdx.x * W < cnt) {
+#pragma unroll
+        for (int k = 0; k < W; k++) s[threadIdx.x * W + k] = reg[k];
+    }
+    __syncthreads();
+    if (sizeof(E) == 4 && ((uintptr_t)(g + base) & 15) == 0) {
+        const int c4 = cnt >> 2;
+        for (int i = threadIdx.x; i < c4; i += BLOCK) reinterpret_cast<float4*>(g + base)[i] = reinterpret_cast<const float4*>(s)[i];
+        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += BLOCK) g[base + i] = s[i];
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += BLOCK) g[base + i] = s[i];
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------- SoA state access
+template <typename T, int NOBJ> __device__ __forceinline__ void load_state(const EnvDev<T>& E, int i, T* q, T* qd, Obj<T>* ob, T* goal) {
+    const int n = E.n;
+#pragma unroll
+    for (int d = 0; d < ND; d++) { q[d] = E.q[d * n + i]; qd[d] = E.qd[d * n + i]; }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        const T* p = E.obj + (size_t)o * 13 * n + i;
+        ob[o].pos = mk<T>(p[0], p[n], p[2 * n]); ob[o].qx = p[3 * n]; ob[o].qy = p[4 * n]; ob[o].qz = p[5 * n]; ob[o].qw = p[6 * n];
+        ob[o].lin = mk<T>(p[7 * n], p[8 * n], p[9 * n]); ob[o].ang = mk<T>(p[10 * n], p[11 * n], p[12 * n]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) goal[k] = E.goal[k * n + i];
+}
+template <typename T, int NOBJ> __device__ __forceinline__ void store_state(const EnvDev<T>& E, int i, const T* q, const T* qd, const Obj<T>* ob) {
+    const int n = E.n;
+#pragma unroll
+    for (int d = 0; d < ND; d++) { E.q[d * n + i] = q[d]; E.qd[d * n + i] = qd[d]; }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        T* p = E.obj + (size_t)o * 13 * n + i;
+        p[0] = ob[o].pos.x; p[n] = ob[o].pos.y; p[2 * n] = ob[o].pos.z; p[3 * n] = ob[o].qx; p[4 * n] = ob[o].qy; p[5 * n] = ob[o].qz; p[6 * n] = ob[o].qw;
+        p[7 * n] = ob[o].lin.x; p[8 * n] = ob[o].lin.y; p[9 * n] = ob[o].lin.z; p[10 * n] = ob[o].ang.x; p[11 * n] = ob[o].ang.y; p[12 * n] = ob[o].ang.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- reset
+// Task.reset + Panda.reset for one env: neutral joints, zero velocity, sampled (or overridden) goal and object placement.
+// Distributions: reach.py:22-23,51-54; push.py:69-87; slide.py:23-24,73-91; pick_and_place.py:65-85; stack.py:94-119;
+// flip.py:63-80 (goal: uniform rotation, drawn from the device stream instead of scipy's unseeded global RNG).
+template <typename T, int TASK>
+__device__ __forceinline__ void env_reset(const EnvDev<T>& E, int i, uint32_t episode, const double* goal_ov, const double* obj_ov, T* q, T* qd, Obj<T>* ob, T* goal) {
+    constexpr int NOBJ = task_nobj(TASK);
+    constexpr int G = task_goal_dim(TASK);
+    const double neutral[ND] = {0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79, 0.00, 0.00};   // panda.py:45
+#pragma unroll
+    for (int d = 0; d < ND; d++) { q[d] = (T)neutral[d]; qd[d] = T(0); }
+    Philox rng(E.seed, (unsigned long long)(E.id0 + i), episode);
+    double g[6] = {0, 0, 0, 0, 0, 0}, op[6] = {0, 0, 0, 0, 0, 0};
+    if (TASK == TASK_REACH) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); g[2] = rng.uniform(0.0, 0.3); }
+    else if (TASK == TASK_PUSH) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); g[2] = 0.02; }
+    else if (TASK == TASK_SLIDE) { g[0] = rng.uniform(0.25, 0.55); g[1] = rng.uniform(-0.15, 0.15); g[2] = 0.03; }
+    else if (TASK == TASK_PICK_AND_PLACE) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); double z = rng.uniform(0.0, 0.2); if (rng.uniform() < 0.3) z = 0.0; g[2] = 0.02 + z; }
+    else if (TASK == TASK_STACK) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); g[2] = 0.02; g[3] = g[0]; g[4] = g[1]; g[5] = 0.06; }
+    else { double a = rng.normal(), b = rng.normal(), c = rng.normal(), d = rng.normal(), nn = 1.0 / sqrt(a * a + b * b + c * c + d * d); g[0] = a * nn; g[1] = b * nn; g[2] = c * nn; g[3] = d * nn; }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        op[3 * o] = rng.uniform(-0.15, 0.15); op[3 * o + 1] = rng.uniform(-0.15, 0.15);
+        op[3 * o + 2] = TASK == TASK_SLIDE ? 0.03 : (o == 1 ? 0.06 : 0.02);
+    }
+    if (goal_ov) {
+#pragma unroll
+        for (int k = 0; k < G; k++) g[k] = goal_ov[(size_t)i * G + k];
+    }
+    if (obj_ov) {
+#pragma unroll
+        for (int k = 0; k < 3 * NOBJ; k++) op[k] = obj_ov[(size_t)i * 3 * NOBJ + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) goal[k] = (T)g[k];
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        ob[o].pos = mk<T>((T)op[3 * o], (T)op[3 * o + 1], (T)op[3 * o + 2]); ob[o].qx = T(0); ob[o].qy = T(0); ob[o].qz = T(0); ob[o].qw = T(1);
+        ob[o].lin = mk<T>(T(0), T(0), T(0)); ob[o].ang = mk<T>(T(0), T(0), T(0));
+    }
+}
+
+template <typename T, int TASK>
+__global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ EnvDev<T> E, const ResetIO io) {
+    constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK);
+    const long long row0 = (long long)blockIdx.x * BLOCK;
+    const int i = (int)row0 + threadIdx.x;
+    const bool valid = i < E.n;
+    const bool mine = valid && (io.mask == nullptr || io.mask[i] != 0);
+    float obs[O], ag[G], dg[G];
+    if (mine) {
+        T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+        uint32_t ep = E.episode[i] + 1u;
+        env_reset<T, TASK>(E, i, ep, io.goal_override, io.object_override, q, qd, ob, goal);
+        store_state<T, NOBJ>(E, i, q, qd, ob);
+#pragma unroll
+        for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
+        E.steps[i] = 0; E.episode[i] = ep; E.ret[i] = 0.0f;
+        env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
+    }
+    tile_store<O>((float*)nullptr, io.obs, row0, E.n, obs, false, mine);
+    tile_store<G>((float*)nullptr, io.ag, row0, E.n, ag, false, mine);
+    tile_store<G>((float*)nullptr, io.dg, row0, E.n, dg, false, mine);
+}
+
+// ---------------------------------------------------------------------------------------------- step
+template <typename T, int TASK, int CTRL>
+__global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ EnvDev<T> E, const StepIO io) {
+    constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
+    __shared__ __align__(16) float s_io[BLOCK * O];
+    __shared__ double s_stats[4];
+    const long long row0 = (long long)blockIdx.x * BLOCK;
+    const int i = (int)row0 + threadIdx.x;
+    const bool valid = i < E.n;
+    if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
+    float act[NA];
+    tile_load<NA>(s_io, io.actions, row0, E.n, act);
+    float obs[O], ag[G], dg[G], reward = 0.0f;
+    unsigned char term = 0, trunc = 0;
+    if (valid) {
+        T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+        Contacts<T> C;
+        load_state<T, NOBJ>(E, i, q, qd, ob, goal);
+        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, obs, ag, dg, reward, term, C);
+        int steps = E.steps[i] + 1;
+        trunc = steps >= task_max_steps(TASK);
+        float ret = E.ret[i] + reward;
+        if (io.auto_reset && (term || trunc)) {
+            atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)term); atomicAdd(&s_stats[2], (double)ret); atomicAdd(&s_stats[3], (double)steps);
+            uint32_t ep = E.episode[i] + 1u;
+            env_reset<T, TASK>(E, i, ep, nullptr, nullptr, q, qd, ob, goal);
+#pragma unroll
+            for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
+            E.episode[i] = ep; steps = 0; ret = 0.0f;
+            env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
+        }
+        store_state<T, NOBJ>(E, i, q, qd, ob);
+        E.steps[i] = steps; E.ret[i] = ret;
+    }
+    tile_store<O>(s_io, io.obs, row0, E.n, obs, true, valid);
+    tile_store<G>(s_io, io.ag, row0, E.n, ag, true, valid);
+    tile_store<G>(s_io, io.dg, row0, E.n, dg, true, valid);
+    if (valid) {
+        if (io.reward) io.reward[i] = reward;
+        if (io.terminated) io.terminated[i] = term;
+        if (io.truncated) io.truncated[i] = trunc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_stats[threadIdx.x] != 0.0) atomicAdd(&E.stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------------------------- raw state exchange / IK
+template <typename T, int TASK>
+__global__ void __launch_bounds__(BLOCK) get_state_kernel(const __grid_constant__ EnvDev<T> E, double* out) {
+    constexpr int NOBJ = task_nobj(TASK), G = task_goal_dim(TASK), SD = 18 + 13 * NOBJ + G + 1;
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n) return;
+    double* r = out + (size_t)i * SD; const int n = E.n;
+    for (int d = 0; d < ND; d++) { r[d] = E.q[d * n + i]; r[9 + d] = E.qd[d * n + i]; }
+    for (int k = 0; k < 13 * NOBJ; k++) r[18 + k] = E.obj[(size_t)k * n + i];
+    for (int k = 0; k < G; k++) r[18 + 13 * NOBJ + k] = E.goal[k * n + i];
+    r[SD - 1] = E.steps[i];
+}
+template <typename T, int TASK>
+__global__ void __launch_bounds__(BLOCK) set_state_kernel(const __grid_constant__ EnvDev<T> E, const double* in, const unsigned char* mask) {
+    constexpr int NOBJ = task_nobj(TASK), G = task_goal_dim(TASK), SD = 18 + 13 * NOBJ + G + 1;
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n || (mask && !mask[i])) return;
+    const double* r = in + (size_t)i * SD; const int n = E.n;
+    for (int d = 0; d < ND; d++) { E.q[d * n + i] = (T)r[d]; E.qd[d * n + i] = (T)r[9 + d]; }
+    for (int k = 0; k < 13 * NOBJ; k++) E.obj[(size_t)k * n + i] = (T)r[18 + k];
+    for (int k = 0; k < G; k++) E.goal[k * n + i] = (T)r[18 + 13 * NOBJ + k];
+    E.steps[i] = (int)r[SD - 1];
+}
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) ik_kernel(const __grid_constant__ EnvDev<T> E, const double* pos, const double* quat, double* out) {
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n) return;
+    T q[ND], tq[4], o[7];
+    for (int d = 0; d < ND; d++) q[d] = E.q[d * E.n + i];
+    double nn = 0; for (int k = 0; k < 4; k++) nn += quat[(size_t)i * 4 + k] * quat[(size_t)i * 4 + k];
+    nn = 1.0 / sqrt(nn);
+    for (int k = 0; k < 4; k++) tq[k] = (T)(quat[(size_t)i * 4 + k] * nn);
+    ik_ee(E.M, q, mk<T>((T)pos[(size_t)i * 3], (T)pos[(size_t)i * 3 + 1], (T)pos[(size_t)i * 3 + 2]), tq, o);
+    for (int d = 0; d < 7; d++) out[(size_t)i * 7 + d] = (double)o[d];
+}
+
+// ---------------------------------------------------------------------------------------------- HER compute_reward / is_success
+// HBM-bound: M rows of two [M,G] arrays in, 4 (reward) or 1 (success) bytes out.  Rows are staged through shared memory with
+// 16-byte loads; 4 row-tiles per block keep enough loads in flight.
+template <typename E, int TASK, bool WANT_REWARD>
+__global__ void __launch_bounds__(BLOCK) reward_kernel(const E* __restrict__ ag, const E* __restrict__ dg, float* __restrict__ reward, unsigned char* __restrict__ success, long long m, int reward_type) {
+    constexpr int G = task_goal_dim(TASK);
+    __shared__ __align__(16) E s_a[BLOCK * G];
+    __shared__ __align__(16) E s_b[BLOCK * G];
+    for (long long row0 = (long long)blockIdx.x * BLOCK; row0 < m; row0 += (long long)gridDim.x * BLOCK) {
+        const long long base = row0 * G;
+        const int rows = (int)min((long long)BLOCK, m - row0), cnt = rows * G;
+        if ((((uintptr_t)(ag + base)) & 15) == 0 && (((uintptr_t)(dg + base)) & 15) == 0) {
+            constexpr int V = 16 / sizeof(E);
+            const int cv = cnt / V;
+            for (int i = threadIdx.x; i < cv; i += BLOCK) {
+                reinterpret_cast<float4*>(s_a)[i] = __ldcs(reinterpret_cast<const float4*>(ag + base) + i);
+                reinterpret_cast<float4*>(s_b)[i] = __ldcs(reinterpret_cast<const float4*>(dg + base) + i);
+            }
+            for (int i = cv * V + threadIdx.x; i < cnt; i += BLOCK) { s_a[i] = ag[base + i]; s_b[i] = dg[base + i]; }
+        } else {
+            for (int i = threadIdx.x; i < cnt; i += BLOCK) { s_a[i] = ag[base + i]; s_b[i] = dg[base + i]; }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < rows) {
+            E a[G], b[G];
+#pragma unroll
+            for (int k = 0; k < G; k++) { a[k] = s_a[threadIdx.x * G + k]; b[k] = s_b[threadIdx.x * G + k]; }
+            E d = goal_distance(TASK, a, b);
+            if (WANT_REWARD) reward[row0 + threadIdx.x] = reward_from_distance(reward_type, d, sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK));
+            else success[row0 + threadIdx.x] = d < (sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK));
+        }
+        __syncthreads();
+    }
+}
+
+// host-side launchers, instantiated per task in panda_step_task.cu
+template <typename T, int TASK> void launch_step(const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st);
+template <typename T, int TASK> void launch_reset(const EnvDev<T>& E, const ResetIO& io, cudaStream_t st);
+template <typename T, int TASK> void launch_get_state(const EnvDev<T>& E, double* out, cudaStream_t st);
+template <typename T, int TASK> void launch_set_state(const EnvDev<T>& E, const double* in, const unsigned char* mask, cudaStream_t st);
+
+}  // namespace pg

