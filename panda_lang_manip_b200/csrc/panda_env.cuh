@@ -63,8 +63,8 @@ PG_HD double goal_distance(int task, const double* a, const double* b) {
     return d_sqrt(acc);
 }
 // sparse: -(d > thr).astype(float32) -> -1.0 or -0.0;  dense: -d.astype(float32)
-PG_HD float reward_from_distance(int reward_type, float d, float thr) { return reward_type == REWARD_SPARSE ? -(d > thr ? 1.0f : 0.0f) : -d; }
-PG_HD float reward_from_distance(int reward_type, double d, double thr) { return reward_type == REWARD_SPARSE ? -(d > thr ? 1.0f : 0.0f) : -(float)d; }
+PG_HD float reward_from_distance(int reward_type, float d, float thr) { return reward_type == REWARD_SPARSE ? (d > thr ? -1.0f : -0.0f) : -d; }
+PG_HD float reward_from_distance(int reward_type, double d, double thr) { return reward_type == REWARD_SPARSE ? (d > thr ? -1.0f : -0.0f) : -(float)d; }
 
 // pybullet getEulerFromQuaternion
 template <typename T> PG_HD void euler_from_quat(T x, T y, T z, T w, T* e) {

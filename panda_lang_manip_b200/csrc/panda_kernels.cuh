@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 template <typename T, int TASK, int CTRL>
 __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ EnvDev<T> E, const StepIO io) {
     constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
-    __shared__ __align__(16) float s_io[BLOCK * O];
+    constexpr int W = O > NA ? (O > G ? O : G) : (NA > G ? NA : G);   // widest row staged through the tile
+    __shared__ __align__(16) float s_io[BLOCK * W];
     __shared__ double s_stats[4];
     const long long row0 = (long long)blockIdx.x * BLOCK;
     const int i = (int)row0 + threadIdx.x;

@@ -1,0 +1,45 @@
+"""The oracle's reward / success / sampling restatement against golden vectors produced by the reference's own code
+(tests/golden/make_golden.py executed /root/reference/panda_gym/{utils.py, envs/tasks/*.py})."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.oracle_util import GOAL_DIM, TASKS, P, load_oracle
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rewards.npz"))
+TASK_NAMES = ["reach", "push", "slide", "pick_and_place", "stack", "flip"]
+
+
+@pytest.mark.parametrize("task", TASK_NAMES)
+@pytest.mark.parametrize("rt", ["sparse", "dense"])
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+def test_reward_and_success_bit_exact(task, rt, dt):
+    lib = load_oracle()
+    k = f"{task}_{rt}_{dt}"
+    ag, dg = np.ascontiguousarray(GOLD[k + "_ag"]), np.ascontiguousarray(GOLD[k + "_dg"])
+    m = ag.shape[0]
+    rew, suc = np.zeros(m, np.float32), np.zeros(m, np.uint8)
+    sfx = "f32" if dt == "float32" else "f64"
+    getattr(lib, "po_compute_reward_" + sfx)(TASKS[task], 0 if rt == "sparse" else 1, P(ag), P(dg), P(rew), m)
+    getattr(lib, "po_is_success_" + sfx)(TASKS[task], P(ag), P(dg), P(suc), m)
+    assert rew.tobytes() == GOLD[k + "_reward"].tobytes()       # includes -0.0 vs +0.0
+    assert np.array_equal(suc.astype(bool), GOLD[k + "_success"])
+
+
+@pytest.mark.parametrize("task", ["reach", "push", "slide", "pick_and_place", "stack"])
+def test_seeded_sampling_contract(task):
+    """core.py:243-244 + Task.reset draw order: the host facade reproduces the reference's seeded goals/objects."""
+    from panda_lang_manip_b200.panda_gym.sampling import sample_reset
+    for seed in range(16):
+        goal, objs = sample_reset(task, np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed))))
+        assert np.array_equal(goal, GOLD[f"{task}_seeded_goals"][seed])
+        if task != "reach":
+            assert np.array_equal(np.concatenate(objs), GOLD[f"{task}_seeded_objects"][seed])
+
+
+def test_utils_distance_golden():
+    from panda_lang_manip_b200.panda_gym import utils
+    assert np.array_equal(utils.distance(GOLD["utils_distance_a"], GOLD["utils_distance_b"]), GOLD["utils_distance"])
+    a, b = GOLD["utils_angle_a"], GOLD["utils_angle_b"]
+    assert np.allclose([utils.angle_distance(a[i], b[i]) for i in range(64)], GOLD["utils_angle_distance_rows"], atol=1e-15)
