@@ -490,15 +490,16 @@ void po_inverse_kinematics(const PoSim *s, int link, const double pos[3], const 
  *   objects: box (8 vertices) or z-cylinder (8 rim points, 4 per cap at 45 deg + k 90 deg);
  *   a contact = a vertex of body A against the signed-distance field of body B (plane / box / cylinder) with
  *   distance < CONTACT_MARGIN (4 mm: twice the largest per-sub-step approach, instead of Bullet's 2 cm breaking threshold,
- *   to bound the row count); at most MAXC contacts (MAXRC on the robot) in collection order; pairs: object-table(+ground plane), robot box-table, robot box<->object (both
+ *   to bound the row count); at most MAXC_* contacts in collection order; pairs: object-table(+ground plane), robot box-table, robot box<->object (both
  *   directions), object<->object (both directions).
  * Rows follow btMultiBodyConstraintSolver::setupMultiBodyContactConstraint: speculative when distance > 0
  * (velocityError -= distance/dt), erp 0.2 when penetrating, friction = product of the two coefficients, two friction
  * directions from btPlaneSpace1 with the implicit cone clamp, finger links soft (stiffness 30000, damping 1000 ->
  * contact erp/cfm, App. B.3), no warm starting. */
 #define CONTACT_MARGIN 0.004
-#define MAXC 24   /* contacts per env and sub-step; later candidates are dropped */
-#define MAXRC 16  /* of which contacts that involve a robot link */
+/* contacts per env and sub-step; later candidates are dropped.  Sized to the solver's on-chip contact store. */
+#define MAXC_ROBOT_ONLY 10
+#define MAXC_OBJECTS 22
 #define CONTACT_ERP 0.2
 #define LINEAR_SLOP 1e-5
 #define GROUND_Z (-0.4)
@@ -580,7 +581,7 @@ static void plane_space(const double *n, double *p, double *q) { /* btPlaneSpace
 /* one contact: point P (world), normal n (world, pointing from B to A), distance; A/B are (link,obj) with -1/-1 = static */
 static void add_contact(PoSim *s, const double *gv, const double *P, const double *n, double dist, int linkA, int objA, int linkB, int objB, double mu, int soft) {
     int on_robot = linkA >= 0 || linkB >= 0;
-    if (s->last_contacts >= MAXC || (on_robot && s->last_robot_contacts >= MAXRC)) return;
+    if (s->last_contacts >= (s->nobj == 0 ? MAXC_ROBOT_ONLY : MAXC_OBJECTS)) return;
     if (on_robot) s->last_robot_contacts++;
     double t1[3], t2[3]; plane_space(n, t1, t2);
     const double *dirs[3] = {n, t1, t2};
@@ -621,7 +622,10 @@ static void collect_contacts(PoSim *s, const double *gv) {
         }
     }
     /* 2. robot box vertices vs table top */
+    /* fingers: only the 4 vertices of the outer face (the side away from the other finger).  Against a plane the lowest point of
+     * the finger pair is always attained there: the inner-face vertices lie between outer vertices of the two fingers. */
     for (int b = 0; b < 3; b++) for (int k = 0; k < 8; k++) {
+        if ((b == 1 && !(k & 2)) || (b == 2 && (k & 2))) continue;
         double v[3], P[3]; box_vertex(RBOX[b].h, k, v); m3mulv(P, Rb[b], v); v3add(P, P, cb[b]);
         if (over_table(s, P) && P[2] < CONTACT_MARGIN) add_contact(s, gv, P, up, P[2], RBOX[b].link, -1, -1, -1, RBOX[b].mu * TABLE_MU, RBOX[b].soft);
     }

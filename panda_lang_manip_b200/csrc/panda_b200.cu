@@ -2,6 +2,7 @@
 // kernel dispatch, the host-buffer entry points and the HER reward kernels.  No CPU fallback: every entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -66,6 +67,7 @@ struct pg_env {
     void* blob = nullptr; size_t blob_bytes = 0;      // one allocation: q, qd, obj, goal, steps, episode, ret, stats
     EnvDev<float> Ef; EnvDev<double> Ed;
     std::map<int, void*> snaps; int next_snap = 0;
+    bool sort_envs = true;                            // PG_SORT_ENVS=0 disables the contact-aware thread->env map (A/B measurements)
     // host-buffer path: pinned staging + device I/O buffers + private stream
     cudaStream_t hstream = nullptr;
     float *h_act = nullptr, *h_out = nullptr; float* d_act = nullptr; float* d_out = nullptr; size_t out_floats = 0; size_t out_bytes = 0;
@@ -81,6 +83,7 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.obj = (T*)take((size_t)(e->nobj > 0 ? e->nobj : 1) * 13 * n * sizeof(T));
     E.goal = (T*)take(6 * n * sizeof(T));
     E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
+    E.ccount = (unsigned char*)take(n); E.perm = (int*)take(n * sizeof(int));
     e->blob_bytes = off;
 }
 
@@ -121,6 +124,7 @@ int pg_create(int task, int control_type, int reward_type, int num_envs, int dev
     cudaMemset(e->blob, 0, e->blob_bytes);
     if (precision == PG_F32) { bind(e->Ef, e, (char*)e->blob, seed, env_id_offset); e->Ef.M = make_model<float>(base); e->Ef.S = make_scene<float>(task); }
     else { bind(e->Ed, e, (char*)e->blob, seed, env_id_offset); e->Ed.M = make_model<double>(base); e->Ed.S = make_scene<double>(task); }
+    { const char* v = getenv("PG_SORT_ENVS"); if (v && v[0] == '0') e->sort_envs = false; }
     *out = e;
     int rc = pg_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc != PG_OK) { pg_destroy(e); *out = nullptr; return rc; }
@@ -163,7 +167,13 @@ int pg_step(pg_env* e, const float* actions, float* obs, float* ag, float* dg, f
     if (!e || !actions) return fail(PG_ERR_ARG, "pg_step: NULL handle or actions");
     PG_CUDA(cudaSetDevice(e->device));
     StepIO io{actions, obs, ag, dg, reward, terminated, truncated, auto_reset};
-    if (e->precision == PG_F32) Dispatch<float>::step(e->task, e->Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, e->Ed, e->ctrl, io, (cudaStream_t)stream);
+    // contact-aware thread -> env map (see perm_kernel); small batches keep the identity map and the tiled I/O path
+    int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
+    const bool use_perm = e->sort_envs && e->n >= 4096;
+    if (use_perm) { perm_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, perm, e->n); g_launches++; }
+    EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
+    if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
+    if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, (cudaStream_t)stream);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

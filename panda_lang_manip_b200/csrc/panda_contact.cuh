@@ -15,8 +15,6 @@
 namespace pg {
 
 constexpr int MAXOBJ = 2;
-constexpr int MAXC = 24;    // contacts per env and sub-step
-constexpr int MAXRC = 16;   // of which on the robot
 
 enum { SH_BOX = 0, SH_CYL = 1 };
 template <typename T> struct Scene {
@@ -113,18 +111,41 @@ template <typename T> PG_HD void plane_space(V3<T> n, V3<T>& p, V3<T>& q) {   //
     }
 }
 
+// ---------------------------------------------------------------------------------------------- contact storage
 // body codes: -1 static, 0..2 robot box (hand / finger 1 / finger 2), 3 + o object o
+// Every robot collision box rides on link 6 (hand) or on a finger that slides on it, so a robot contact row never needs its
+// 9-wide joint Jacobian: it is a wrench w (8 numbers: moment about the link-6 origin, force, the two finger-slide components)
+// in the 8-dimensional operational space x = [omega6, v6, q7', q8'] = Jx q', and the solver works on that space's inverse
+// inertia Lambda = Jx M^-1 Jx^T (8x8, registers).  A contact record is then pure geometry + 3 x (1/D, rhs, impulse): 17 words.
+// Records and Jx live in shared memory, word-interleaved by thread (bank-conflict free).
+constexpr int REC = 17;                 // words per contact record
+constexpr int JX_SLOTS = 42;            // Jx: per arm joint j, angular (z_j) and linear (z_j x (O6 - p_j)) columns
+// contacts per env and sub-step (later candidates are dropped; the oracle applies the same cap): robot-only scenes keep two
+// 128-thread blocks per SM, scenes with objects take the whole SM's shared memory for one block
+PG_HD constexpr int max_contacts(int nobj) { return nobj == 0 ? 10 : 22; }
+PG_HD constexpr int solver_slots(int nobj) { return JX_SLOTS + max_contacts(nobj) * REC; }
+enum { C_P = 0, C_N = 3, C_INVD = 6, C_RHS = 9, C_APP = 12, C_MU = 15, C_CODE = 16 };
+
+template <typename T> struct CStore {   // per-thread view of the shared-memory slab (host test build: a plain array, stride 1)
+    T* base; int stride;
+    PG_HD T& at(int slot) const { return base[slot * stride]; }
+};
 template <typename T> struct Contacts {
-    int n, nr;
-    T P[MAXC][3], D[MAXC][3][3];            // point, directions (normal, t1, t2)
-    signed char a[MAXC], b[MAXC], ri[MAXC]; // bodies, robot-pool slot (-1: none)
-    T invD[MAXC][3], rhs[MAXC][3], app[MAXC][3], mu[MAXC], cfm[MAXC];
-    T Jr[MAXRC][3][ND], Wr[MAXRC][3][ND];
+    CStore<T> st;
+    int n, nr, cap;
+    PG_HD T& f(int c, int k) { return st.at(JX_SLOTS + c * REC + k); }
+    PG_HD T& jx(int j, int a) { return st.at(6 * j + a); }
+};
+PG_HD constexpr int sidx(int a, int b) { return a <= b ? a * 8 - a * (a - 1) / 2 + (b - a) : b * 8 - b * (b - 1) / 2 + (a - b); }
+template <typename T> struct OpSpace {
+    T L[36];            // Lambda, symmetric 8x8 packed by sidx
+    T v[8];             // Jx * qd (current operational-space velocity)
+    V3<T> O6, hy;       // link-6 origin, hand y axis (finger slide direction) in the world
 };
 
 template <typename T, int NOBJ> struct World {
     Frame<T> F[7];              // arm link frames at the sub-step's q
-    Rot<T> Rb[3]; V3<T> cb[3];  // robot collision boxes in the world
+    Rot<T> Rb; V3<T> cb[3];     // robot collision boxes in the world (all three share the hand's orientation)
     Rot<T> Ro[NOBJ > 0 ? NOBJ : 1];
     T Iinv[NOBJ > 0 ? NOBJ : 1][6];   // world inverse inertia (xx,xy,xz,yy,yz,zz)
 };
@@ -132,96 +153,51 @@ template <typename T> PG_HD V3<T> sym6_mul(const T* I, V3<T> w) {
     return mk<T>(I[0] * w.x + I[1] * w.y + I[2] * w.z, I[1] * w.x + I[3] * w.y + I[4] * w.z, I[2] * w.x + I[4] * w.y + I[5] * w.z);
 }
 
-// robot part of the Jacobian row of a unit force `d` at world point P on robot box rb (0 hand, 1/2 fingers)
-template <typename T, int NOBJ> PG_HD void robot_point_jac(const World<T, NOBJ>& W, int rb, V3<T> P, V3<T> d, T sign, T* J) {
-#pragma unroll
-    for (int j = 0; j < 7; j++) J[j] = sign * dot(W.F[j].Z, cross(P - W.F[j].p, d));
-    const T k = Consts<T>::k45;
-    V3<T> hy = (W.F[6].X + W.F[6].Y) * k;   // hand y axis in the world
-    T fd = dot(hy, d);
-    J[7] = rb == 1 ? sign * fd : T(0);
-    J[8] = rb == 2 ? -sign * fd : T(0);
-}
-
-template <typename T, int NOBJ>
-PG_HD void add_contact(const Scene<T>& S, const World<T, NOBJ>& W, const T (*Minv)[ND], const T* qd, const Obj<T>* ob, Contacts<T>& C,
-                       V3<T> P, V3<T> n, T dist, int A, int B, T mu, bool soft) {
+// geometry only: the rows are set up once the operational space is known
+template <typename T>
+PG_HD void add_contact(Contacts<T>& C, V3<T> P, V3<T> n, T dist, int A, int B, T mu, bool soft, bool table = false) {
     bool on_robot = (A >= 0 && A < 3) || (B >= 0 && B < 3);
-    if (C.n >= MAXC || (on_robot && C.nr >= MAXRC)) return;
+    if (C.n >= C.cap) return;
     int c = C.n++;
-    int ri = -1;
-    if (on_robot) ri = C.nr++;
-    C.ri[c] = (signed char)ri; C.a[c] = (signed char)A; C.b[c] = (signed char)B; C.mu[c] = mu;
-    C.P[c][0] = P.x; C.P[c][1] = P.y; C.P[c][2] = P.z;
-    V3<T> t1, t2; plane_space(n, t1, t2);
-    T erp = soft ? S.soft_erp : Consts<T>::erp, cfm = soft ? S.soft_cfm : T(0);
-    C.cfm[c] = cfm;
-#pragma unroll 1
-    for (int k = 0; k < 3; k++) {
-        V3<T> d = k == 0 ? n : (k == 1 ? t1 : t2);
-        C.D[c][k][0] = d.x; C.D[c][k][1] = d.y; C.D[c][k][2] = d.z;
-        T den = T(0), rel = T(0);
-        if (on_robot) {
-            T J[ND];
-            if (A >= 0 && A < 3) robot_point_jac(W, A, P, d, T(1), J); else robot_point_jac(W, B, P, d, T(-1), J);
-#pragma unroll
-            for (int i = 0; i < ND; i++) {
-                T w = T(0);
-#pragma unroll
-                for (int j = 0; j < ND; j++) w += Minv[i][j] * J[j];
-                C.Jr[ri][k][i] = J[i]; C.Wr[ri][k][i] = w;
-                den += J[i] * w; rel += J[i] * qd[i];
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < NOBJ; o++) {
-            T sg = (A == 3 + o) ? T(1) : ((B == 3 + o) ? T(-1) : T(0));
-            if (sg != T(0)) {
-                V3<T> r = P - ob[o].pos, rxd = cross(r, d);
-                den += T(1) / S.mass[o] + dot(rxd, sym6_mul(W.Iinv[o], rxd));
-                rel += sg * dot(d, ob[o].lin + cross(ob[o].ang, r));
-            }
-        }
-        if (k == 0) {
-            T inv = T(1) / (den + cfm);
-            T pen = dist + T(1e-5), poserr = T(0), velerr = -rel;
-            if (pen > 0) velerr -= pen * Consts<T>::inv_dt; else poserr = -pen * erp * Consts<T>::inv_dt;
-            C.invD[c][0] = inv; C.rhs[c][0] = (poserr + velerr) * inv;
-        } else {
-            T inv = T(1) / den;
-            C.invD[c][k] = inv; C.rhs[c][k] = -rel * inv;
-        }
-        C.app[c][k] = T(0);
-    }
+    if (on_robot) C.nr++;
+    C.f(c, C_P) = P.x; C.f(c, C_P + 1) = P.y; C.f(c, C_P + 2) = P.z;
+    C.f(c, C_N) = n.x; C.f(c, C_N + 1) = n.y; C.f(c, C_N + 2) = n.z;
+    C.f(c, C_RHS) = dist;       // parked here until rows_setup
+    C.f(c, C_MU) = mu;
+    C.f(c, C_CODE) = (T)((A + 1) + 8 * (B + 1) + (soft ? 64 : 0) + (table ? 128 : 0));
 }
 
-template <typename T, int NOBJ> PG_HD bool over_table(const Scene<T>& S, V3<T> p) { return p.x >= S.table_x0 && p.x <= S.table_x1 && p.y >= S.table_y0 && p.y <= S.table_y1; }
+template <typename T> PG_HD bool over_table(const Scene<T>& S, V3<T> p) { return p.x >= S.table_x0 && p.x <= S.table_x1 && p.y >= S.table_y0 && p.y <= S.table_y1; }
 
 template <typename T, int NOBJ>
-PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const T (*Minv)[ND], const T* qd, const Obj<T>* ob, Contacts<T>& C) {
-    C.n = 0; C.nr = 0;
+PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Obj<T>* ob, Contacts<T>& C) {
+    C.n = 0; C.nr = 0; C.cap = max_contacts(NOBJ);
     const V3<T> up = mk<T>(T(0), T(0), T(1));
     // 1. object vertices against the table top / ground plane
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) {
         for (int k = 0; k < 8; k++) {
             V3<T> P = rot_mul(W.Ro[o], obj_vertex(S, o, k)) + ob[o].pos;
-            T plane = (over_table<T, NOBJ>(S, P) && P.z > T(-0.05)) ? T(0) : S.ground_z;
+            T plane = (over_table(S, P) && P.z > T(-0.05)) ? T(0) : S.ground_z;
             T d = P.z - plane;
-            if (d < S.margin) add_contact<T, NOBJ>(S, W, Minv, qd, ob, C, P, up, d, 3 + o, -1, S.mu[o] * S.table_mu, false);
+            if (d < S.margin) add_contact(C, P, up, d, 3 + o, -1, S.mu[o] * S.table_mu, false);
         }
     }
     // 2. robot box vertices against the table top
+#pragma unroll
     for (int b = 0; b < 3; b++) {
-        T lowest = W.cb[b].z - (fabs(W.Rb[b].X.z) * S.rb_h[b][0] + fabs(W.Rb[b].Y.z) * S.rb_h[b][1] + fabs(W.Rb[b].Z.z) * S.rb_h[b][2]);
+        T lowest = W.cb[b].z - (fabs(W.Rb.X.z) * S.rb_h[b][0] + fabs(W.Rb.Y.z) * S.rb_h[b][1] + fabs(W.Rb.Z.z) * S.rb_h[b][2]);
         if (lowest >= S.margin) continue;
         for (int k = 0; k < 8; k++) {
-            V3<T> P = rot_mul(W.Rb[b], box_vertex(S.rb_h[b], k)) + W.cb[b];
-            if (over_table<T, NOBJ>(S, P) && P.z < S.margin) add_contact<T, NOBJ>(S, W, Minv, qd, ob, C, P, up, P.z, b, -1, S.rb_mu[b] * S.table_mu, b > 0);
+            // fingers: outer-face vertices only (against a plane the inner-face vertices of the pair are never the lowest points)
+            if ((b == 1 && !(k & 2)) || (b == 2 && (k & 2))) continue;
+            V3<T> P = rot_mul(W.Rb, box_vertex(S.rb_h[b], k)) + W.cb[b];
+            if (over_table(S, P) && P.z < S.margin) add_contact(C, P, up, P.z, b, -1, S.rb_mu[b] * S.table_mu, b > 0, true);
         }
     }
     // 3. robot box <-> object, both directions
     if (NOBJ > 0) {
+#pragma unroll
         for (int b = 0; b < 3; b++) {
             T rbr = sqrt(S.rb_h[b][0] * S.rb_h[b][0] + S.rb_h[b][1] * S.rb_h[b][1] + S.rb_h[b][2] * S.rb_h[b][2]);
 #pragma unroll
@@ -230,16 +206,16 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const T 
                 if (norm(W.cb[b] - ob[o].pos) > rbr + orad + S.margin) continue;
                 T mu = S.rb_mu[b] * S.mu[o];
                 for (int k = 0; k < 8; k++) {
-                    V3<T> P = rot_mul(W.Rb[b], box_vertex(S.rb_h[b], k)) + W.cb[b];
+                    V3<T> P = rot_mul(W.Rb, box_vertex(S.rb_h[b], k)) + W.cb[b];
                     V3<T> nl, pl = rot_tmul(W.Ro[o], P - ob[o].pos);
                     T d = obj_sdf(S, o, pl, nl);
-                    if (d < S.margin) add_contact<T, NOBJ>(S, W, Minv, qd, ob, C, P, rot_mul(W.Ro[o], nl), d, b, 3 + o, mu, b > 0);
+                    if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[o], nl), d, b, 3 + o, mu, b > 0);
                 }
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Ro[o], obj_vertex(S, o, k)) + ob[o].pos;
-                    V3<T> nl, pl = rot_tmul(W.Rb[b], P - W.cb[b]);
+                    V3<T> nl, pl = rot_tmul(W.Rb, P - W.cb[b]);
                     T d = sdf_box(S.rb_h[b], pl, nl);
-                    if (d < S.margin) add_contact<T, NOBJ>(S, W, Minv, qd, ob, C, P, rot_mul(W.Rb[b], nl), d, 3 + o, b, mu, b > 0);
+                    if (d < S.margin) add_contact(C, P, rot_mul(W.Rb, nl), d, 3 + o, b, mu, b > 0);
                 }
             }
         }
@@ -249,51 +225,190 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const T 
         T r0 = sqrt(S.half[0][0] * S.half[0][0] + S.half[0][1] * S.half[0][1] + S.half[0][2] * S.half[0][2]);
         T r1 = sqrt(S.half[1][0] * S.half[1][0] + S.half[1][1] * S.half[1][1] + S.half[1][2] * S.half[1][2]);
         if (norm(ob[0].pos - ob[NOBJ - 1].pos) <= r0 + r1 + S.margin) {
+#pragma unroll
             for (int a = 0; a < 2; a++) {
-                int b = 1 - a;
+                const int b = 1 - a;
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Ro[a % NOBJ], obj_vertex(S, a, k)) + ob[a % NOBJ].pos;
                     V3<T> nl, pl = rot_tmul(W.Ro[b % NOBJ], P - ob[b % NOBJ].pos);
                     T d = obj_sdf(S, b, pl, nl);
-                    if (d < S.margin) add_contact<T, NOBJ>(S, W, Minv, qd, ob, C, P, rot_mul(W.Ro[b % NOBJ], nl), d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
+                    if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[b % NOBJ], nl), d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
                 }
             }
         }
     }
 }
 
-// J . dv of row (c, k)
+// operational space of the gripper: Jx into the store, Lambda = Jx M^-1 Jx^T and v = Jx qd into registers
 template <typename T, int NOBJ>
-PG_HD T row_jdv(const Contacts<T>& C, int c, int k, const T* dvq, const V3<T>* dvl, const V3<T>* dva, const Obj<T>* ob) {
+PG_HD void opspace_setup(const World<T, NOBJ>& W, const T (*Minv)[ND], const T* qd, Contacts<T>& C, OpSpace<T>& Op) {
+    Op.O6 = W.F[6].p;
+    Op.hy = (W.F[6].X + W.F[6].Y) * Consts<T>::k45;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        V3<T> z = W.F[j].Z, l = cross(z, Op.O6 - W.F[j].p);
+        C.jx(j, 0) = z.x; C.jx(j, 1) = z.y; C.jx(j, 2) = z.z; C.jx(j, 3) = l.x; C.jx(j, 4) = l.y; C.jx(j, 5) = l.z;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        T row[7], Y[ND], va = T(0);
+#pragma unroll
+        for (int j = 0; j < 7; j++) { row[j] = C.jx(j, a); va += row[j] * qd[j]; }
+        Op.v[a] = va;
+#pragma unroll
+        for (int k = 0; k < ND; k++) {
+            T t = T(0);
+#pragma unroll
+            for (int j = 0; j < 7; j++) t += row[j] * Minv[j][k];
+            Y[k] = t;
+        }
+#pragma unroll
+        for (int b = a; b < 6; b++) {
+            T t = T(0);
+#pragma unroll
+            for (int k = 0; k < 7; k++) t += Y[k] * C.jx(k, b);
+            Op.L[sidx(a, b)] = t;
+        }
+        Op.L[sidx(a, 6)] = Y[7]; Op.L[sidx(a, 7)] = Y[8];
+    }
+    Op.L[sidx(6, 6)] = Minv[7][7]; Op.L[sidx(6, 7)] = Minv[7][8]; Op.L[sidx(7, 7)] = Minv[8][8];
+    Op.v[6] = qd[7]; Op.v[7] = qd[8];
+}
+
+// per-contact decode shared by its three rows
+template <typename T, int NOBJ> struct ContactCtx {
+    V3<T> P, n;
+    int rb;                     // robot box (-1: none)
+    T s;                        // +1: the robot is body A, -1: body B
+    T sgo[NOBJ > 0 ? NOBJ : 1]; // sign of object o in this contact (0: not involved)
+    bool soft;
+    bool table;                 // robot box against the table plane: normal +z, tangents -y, +x (axis-aligned sparse wrenches)
+};
+template <typename T, int NOBJ> PG_HD ContactCtx<T, NOBJ> contact_ctx(Contacts<T>& C, int c) {
+    ContactCtx<T, NOBJ> X;
+    X.P = mk<T>(C.f(c, C_P), C.f(c, C_P + 1), C.f(c, C_P + 2));
+    X.n = mk<T>(C.f(c, C_N), C.f(c, C_N + 1), C.f(c, C_N + 2));
+    int code = (int)C.f(c, C_CODE);
+    int A = (code & 7) - 1, B = ((code >> 3) & 7) - 1;
+    X.soft = (code & 64) != 0; X.table = (code & 128) != 0;
+    X.rb = (A >= 0 && A < 3) ? A : ((B >= 0 && B < 3) ? B : -1);
+    X.s = (A >= 0 && A < 3) ? T(1) : T(-1);
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) X.sgo[o] = (A == 3 + o) ? T(1) : ((B == 3 + o) ? T(-1) : T(0));
+    return X;
+}
+template <typename T, int NOBJ> PG_HD void robot_wrench(const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, V3<T> d, T* w) {
+    V3<T> m = cross(X.P - Op.O6, d);
+    T fd = dot(Op.hy, d);
+    w[0] = X.s * m.x; w[1] = X.s * m.y; w[2] = X.s * m.z; w[3] = X.s * d.x; w[4] = X.s * d.y; w[5] = X.s * d.z;
+    w[6] = X.rb == 1 ? X.s * fd : T(0);
+    w[7] = X.rb == 2 ? -X.s * fd : T(0);
+}
+template <typename T> PG_HD void lambda_mul(const OpSpace<T>& Op, const T* w, T* y) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        T t = T(0);
+#pragma unroll
+        for (int b = 0; b < 8; b++) t += Op.L[sidx(a, b)] * w[b];
+        y[a] = t;
+    }
+}
+// Sparse wrench of a robot-vs-table row: direction SG * e_AX, robot is body A.  Non-zeros: two moment components, one force
+// component, one finger-slide component.
+template <int AX, int SG, typename T, int NOBJ> struct AxisRow {
+    static constexpr int I1 = (AX + 1) % 3, I2 = (AX + 2) % 3;     // r x e_AX = r[I2] e_I1 - r[I1] e_I2
+    T m1, m2, f6, f7;
+    PG_HD AxisRow(const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X) {
+        V3<T> r = X.P - Op.O6;
+        const T rr[3] = {r.x, r.y, r.z}, hh[3] = {Op.hy.x, Op.hy.y, Op.hy.z};
+        m1 = T(SG) * rr[I2]; m2 = T(-SG) * rr[I1];
+        T fd = T(SG) * hh[AX];
+        f6 = X.rb == 1 ? fd : T(0); f7 = X.rb == 2 ? -fd : T(0);
+    }
+    PG_HD T jdv(const T* d8) const { return m1 * d8[I1] + m2 * d8[I2] + T(SG) * d8[3 + AX] + f6 * d8[6] + f7 * d8[7]; }
+    PG_HD void lam(const OpSpace<T>& Op, T* y) const {
+#pragma unroll
+        for (int k = 0; k < 8; k++) y[k] = Op.L[sidx(k, I1)] * m1 + Op.L[sidx(k, I2)] * m2 + T(SG) * Op.L[sidx(k, 3 + AX)] + Op.L[sidx(k, 6)] * f6 + Op.L[sidx(k, 7)] * f7;
+    }
+    PG_HD void apply(const OpSpace<T>& Op, T di, T* d8, T* F8) const {
+        T y[8]; lam(Op, y);
+#pragma unroll
+        for (int k = 0; k < 8; k++) d8[k] += y[k] * di;
+        F8[I1] += m1 * di; F8[I2] += m2 * di; F8[3 + AX] += T(SG) * di; F8[6] += f6 * di; F8[7] += f7 * di;
+    }
+    PG_HD T den(const OpSpace<T>& Op) const { T y[8]; lam(Op, y); return jdv(y); }
+};
+template <typename T> PG_HD T dot8(const T* a, const T* b) {
+    T t = T(0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += a[i] * b[i];
+    return t;
+}
+
+// 1/D and rhs of the three rows of every contact (setupMultiBodyContactConstraint: speculative when separated, ERP when penetrating)
+template <typename T, int NOBJ>
+PG_HD void rows_setup(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const Obj<T>* ob, Contacts<T>& C) {
+    for (int c = 0; c < C.n; c++) {
+        ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
+        T dist = C.f(c, C_RHS);
+        V3<T> t1, t2; plane_space(X.n, t1, t2);
+        T erp = X.soft ? S.soft_erp : Consts<T>::erp, cfm = X.soft ? S.soft_cfm : T(0);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            V3<T> d = k == 0 ? X.n : (k == 1 ? t1 : t2);
+            T den = T(0), rel = T(0);
+            if (NOBJ == 0 || X.table) {
+                if (k == 0) { AxisRow<2, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+                else if (k == 1) { AxisRow<1, -1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+                else { AxisRow<0, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+            } else if (X.rb >= 0) { T w[8], y[8]; robot_wrench<T, NOBJ>(Op, X, d, w); lambda_mul(Op, w, y); den += dot8(w, y); rel += dot8(w, Op.v); }
+#pragma unroll
+            for (int o = 0; o < NOBJ; o++) {
+                if (X.sgo[o] != T(0)) {
+                    V3<T> r = X.P - ob[o].pos, rxd = cross(r, d);
+                    den += T(1) / S.mass[o] + dot(rxd, sym6_mul(W.Iinv[o], rxd));
+                    rel += X.sgo[o] * dot(d, ob[o].lin + cross(ob[o].ang, r));
+                }
+            }
+            if (k == 0) {
+                T inv = T(1) / (den + cfm);
+                T pen = dist + T(1e-5), poserr = T(0), velerr = -rel;
+                if (pen > 0) velerr -= pen * Consts<T>::inv_dt; else poserr = -pen * erp * Consts<T>::inv_dt;
+                C.f(c, C_INVD) = inv; C.f(c, C_RHS) = (poserr + velerr) * inv;
+            } else {
+                T inv = T(1) / den;
+                C.f(c, C_INVD + k) = inv; C.f(c, C_RHS + k) = -rel * inv;
+            }
+            C.f(c, C_APP + k) = T(0);
+        }
+    }
+}
+
+// J . dv of a row along direction d
+template <typename T, int NOBJ>
+PG_HD T row_jdv(const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, V3<T> d, const T* w, const T* d8, const V3<T>* dvl, const V3<T>* dva, const Obj<T>* ob) {
     T jd = T(0);
-    int ri = C.ri[c];
-    if (ri >= 0) {
+    if (X.rb >= 0) jd += dot8(w, d8);
 #pragma unroll
-        for (int i = 0; i < ND; i++) jd += C.Jr[ri][k][i] * dvq[i];
-    }
-    V3<T> d = mk<T>(C.D[c][k][0], C.D[c][k][1], C.D[c][k][2]);
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) {
-        T sg = (C.a[c] == 3 + o) ? T(1) : ((C.b[c] == 3 + o) ? T(-1) : T(0));
-        if (sg != T(0)) { V3<T> r = mk<T>(C.P[c][0], C.P[c][1], C.P[c][2]) - ob[o].pos; jd += sg * dot(d, dvl[o] + cross(dva[o], r)); }
-    }
+    for (int o = 0; o < NOBJ; o++) if (X.sgo[o] != T(0)) jd += X.sgo[o] * dot(d, dvl[o] + cross(dva[o], X.P - ob[o].pos));
     return jd;
 }
 template <typename T, int NOBJ>
-PG_HD void row_apply(const Scene<T>& S, const World<T, NOBJ>& W, const Contacts<T>& C, int c, int k, T di, T* dvq, V3<T>* dvl, V3<T>* dva, const Obj<T>* ob) {
-    int ri = C.ri[c];
-    if (ri >= 0) {
+PG_HD void row_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, V3<T> d, const T* w, T di,
+                     T* d8, T* F8, V3<T>* dvl, V3<T>* dva, const Obj<T>* ob) {
+    if (X.rb >= 0) {
+        T wi[8], y[8];
 #pragma unroll
-        for (int i = 0; i < ND; i++) dvq[i] += C.Wr[ri][k][i] * di;
+        for (int i = 0; i < 8; i++) { wi[i] = w[i] * di; F8[i] += wi[i]; }
+        lambda_mul(Op, wi, y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) d8[i] += y[i];
     }
-    V3<T> d = mk<T>(C.D[c][k][0], C.D[c][k][1], C.D[c][k][2]);
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) {
-        T sg = (C.a[c] == 3 + o) ? T(1) : ((C.b[c] == 3 + o) ? T(-1) : T(0));
-        if (sg != T(0)) {
-            V3<T> r = mk<T>(C.P[c][0], C.P[c][1], C.P[c][2]) - ob[o].pos;
-            dvl[o] = dvl[o] + d * (sg * di / S.mass[o]);
-            dva[o] = dva[o] + sym6_mul(W.Iinv[o], cross(r, d)) * (sg * di);
+        if (X.sgo[o] != T(0)) {
+            dvl[o] = dvl[o] + d * (X.sgo[o] * di / S.mass[o]);
+            dva[o] = dva[o] + sym6_mul(W.Iinv[o], cross(X.P - ob[o].pos, d)) * (X.sgo[o] * di);
         }
     }
 }
@@ -315,15 +430,12 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
         W.F[3] = fk_next<3>(M, W.F[2], sn[3], cs[3]); W.F[4] = fk_next<4>(M, W.F[3], sn[4], cs[4]); W.F[5] = fk_next<5>(M, W.F[4], sn[5], cs[5]);
         W.F[6] = fk_next<6>(M, W.F[5], sn[6], cs[6]);
         const T k = Consts<T>::k45;
-        Rot<T> Rh; Rh.X = (W.F[6].X - W.F[6].Y) * k; Rh.Y = (W.F[6].X + W.F[6].Y) * k; Rh.Z = W.F[6].Z;
+        W.Rb.X = (W.F[6].X - W.F[6].Y) * k; W.Rb.Y = (W.F[6].X + W.F[6].Y) * k; W.Rb.Z = W.F[6].Z;
         V3<T> ph = W.F[6].p + W.F[6].Z * (M.hz - T(0.0584));   // hand frame origin
         V3<T> pf = W.F[6].p + W.F[6].Z * M.hz;
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-            W.Rb[b] = Rh;
-            V3<T> o = b == 0 ? ph : (b == 1 ? pf + Rh.Y * q[7] : pf - Rh.Y * q[8]);
-            W.cb[b] = o + rot_mul(Rh, ld3(S.rb_c[b]));
-        }
+        W.cb[0] = ph + rot_mul(W.Rb, ld3(S.rb_c[0]));
+        W.cb[1] = pf + W.Rb.Y * q[7] + rot_mul(W.Rb, ld3(S.rb_c[1]));
+        W.cb[2] = pf - W.Rb.Y * q[8] + rot_mul(W.Rb, ld3(S.rb_c[2]));
     }
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) {
@@ -340,7 +452,11 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
     }
     JointRows<T> R;
     joint_rows_setup(M, q, qd, target, Minv, R);
-    collect_contacts<T, NOBJ>(S, W, Minv, qd, ob, C);
+    collect_contacts<T, NOBJ>(S, W, ob, C);
+    OpSpace<T> Op;
+    const bool robot_contacts = C.nr > 0;
+    if (robot_contacts) opspace_setup<T, NOBJ>(W, Minv, qd, C, Op);
+    rows_setup<T, NOBJ>(S, W, Op, ob, C);
 
     T dvq[ND];
     V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
@@ -352,30 +468,88 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
     for (int it = 0; it < 50; it++) {
         T res = T(0);
         joint_rows_sweep(M, Minv, R, dvq, it, res);
-        for (int c = 0; c < nc; c++) {          // contact normals
-            T jd = row_jdv<T, NOBJ>(C, c, 0, dvq, dvl, dva, ob);
-            T app = C.app[c][0];
-            T di = C.rhs[c][0] - app * C.cfm[c] - jd * C.invD[c][0];
-            T sum = app + di;
-            if (sum < T(0)) { di = -app; sum = T(0); }
-            C.app[c][0] = sum;
-            row_apply<T, NOBJ>(S, W, C, c, 0, di, dvq, dvl, dva, ob);
-            T r = di / C.invD[c][0]; res = fmax(res, r * r);
-        }
-        for (int c = 0; c < nc; c++) {          // implicit friction cone over the two tangent rows
-            T napp = C.app[c][0];
-            if (napp <= T(0)) continue;
-            T j1 = row_jdv<T, NOBJ>(C, c, 1, dvq, dvl, dva, ob), j2 = row_jdv<T, NOBJ>(C, c, 2, dvq, dvl, dva, ob);
-            T a1 = C.app[c][1], a2 = C.app[c][2];
-            T s1 = a1 + C.rhs[c][1] - j1 * C.invD[c][1], s2 = a2 + C.rhs[c][2] - j2 * C.invD[c][2];
-            T lim = C.mu[c] * napp, len = sqrt(s1 * s1 + s2 * s2);
-            if (len > lim) { T f = lim / len; s1 *= f; s2 *= f; }
-            T d1 = s1 - a1, d2 = s2 - a2;
-            C.app[c][1] = s1; C.app[c][2] = s2;
-            row_apply<T, NOBJ>(S, W, C, c, 1, d1, dvq, dvl, dva, ob);
-            row_apply<T, NOBJ>(S, W, C, c, 2, d2, dvq, dvl, dva, ob);
-            T r1 = d1 / C.invD[c][1], r2 = d2 / C.invD[c][2];
-            res = fmax(res, fmax(r1 * r1, r2 * r2));
+        if (nc > 0) {
+            T d8[8], F8[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) { d8[a] = T(0); F8[a] = T(0); }
+            if (robot_contacts) {       // operational-space velocity change so far: Jx dvq
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+#pragma unroll
+                    for (int a = 0; a < 6; a++) d8[a] += C.jx(j, a) * dvq[j];
+                }
+                d8[6] = dvq[7]; d8[7] = dvq[8];
+            }
+            for (int c = 0; c < nc; c++) {          // contact normals
+                ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
+                T app = C.f(c, C_APP), inv = C.f(c, C_INVD), di;
+                if (NOBJ == 0 || X.table) {
+                    AxisRow<2, 1, T, NOBJ> row(Op, X);
+                    di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm : T(0)) - row.jdv(d8) * inv;
+                    T sum = app + di;
+                    if (sum < T(0)) { di = -app; sum = T(0); }
+                    C.f(c, C_APP) = sum;
+                    row.apply(Op, di, d8, F8);
+                } else {
+                    T w[8];
+                    if (X.rb >= 0) robot_wrench<T, NOBJ>(Op, X, X.n, w);
+                    T jd = row_jdv<T, NOBJ>(Op, X, X.n, w, d8, dvl, dva, ob);
+                    di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm : T(0)) - jd * inv;
+                    T sum = app + di;
+                    if (sum < T(0)) { di = -app; sum = T(0); }
+                    C.f(c, C_APP) = sum;
+                    row_apply<T, NOBJ>(S, W, Op, X, X.n, w, di, d8, F8, dvl, dva, ob);
+                }
+                T r = di / inv; res = fmax(res, r * r);
+            }
+            for (int c = 0; c < nc; c++) {          // implicit friction cone over the two tangent rows
+                T napp = C.f(c, C_APP);
+                if (napp <= T(0)) continue;
+                ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
+                T a1 = C.f(c, C_APP + 1), a2 = C.f(c, C_APP + 2), i1 = C.f(c, C_INVD + 1), i2 = C.f(c, C_INVD + 2);
+                T lim = C.f(c, C_MU) * napp, d1, d2;
+                if (NOBJ == 0 || X.table) {
+                    AxisRow<1, -1, T, NOBJ> r1(Op, X); AxisRow<0, 1, T, NOBJ> r2(Op, X);
+                    T s1 = a1 + C.f(c, C_RHS + 1) - r1.jdv(d8) * i1, s2 = a2 + C.f(c, C_RHS + 2) - r2.jdv(d8) * i2;
+                    T len = sqrt(s1 * s1 + s2 * s2);
+                    if (len > lim) { T f = lim / len; s1 *= f; s2 *= f; }
+                    d1 = s1 - a1; d2 = s2 - a2;
+                    C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
+                    r1.apply(Op, d1, d8, F8); r2.apply(Op, d2, d8, F8);
+                } else {
+                    V3<T> t1, t2; plane_space(X.n, t1, t2);
+                    T w1[8], w2[8];
+                    if (X.rb >= 0) { robot_wrench<T, NOBJ>(Op, X, t1, w1); robot_wrench<T, NOBJ>(Op, X, t2, w2); }
+                    T j1 = row_jdv<T, NOBJ>(Op, X, t1, w1, d8, dvl, dva, ob), j2 = row_jdv<T, NOBJ>(Op, X, t2, w2, d8, dvl, dva, ob);
+                    T s1 = a1 + C.f(c, C_RHS + 1) - j1 * i1, s2 = a2 + C.f(c, C_RHS + 2) - j2 * i2;
+                    T len = sqrt(s1 * s1 + s2 * s2);
+                    if (len > lim) { T f = lim / len; s1 *= f; s2 *= f; }
+                    d1 = s1 - a1; d2 = s2 - a2;
+                    C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
+                    row_apply<T, NOBJ>(S, W, Op, X, t1, w1, d1, d8, F8, dvl, dva, ob);
+                    row_apply<T, NOBJ>(S, W, Op, X, t2, w2, d2, d8, F8, dvl, dva, ob);
+                }
+                T r1 = d1 / i1, r2 = d2 / i2;
+                res = fmax(res, fmax(r1 * r1, r2 * r2));
+            }
+            if (robot_contacts) {       // fold this sweep's contact wrench back into the joint velocities: dvq += M^-1 Jx^T F8
+                T tau[ND];
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    T t = T(0);
+#pragma unroll
+                    for (int a = 0; a < 6; a++) t += C.jx(j, a) * F8[a];
+                    tau[j] = t;
+                }
+                tau[7] = F8[6]; tau[8] = F8[7];
+#pragma unroll
+                for (int i = 0; i < ND; i++) {
+                    T t = T(0);
+#pragma unroll
+                    for (int j = 0; j < ND; j++) t += Minv[i][j] * tau[j];
+                    dvq[i] += t;
+                }
+            }
         }
         if (res <= T(1e-7)) break;
     }

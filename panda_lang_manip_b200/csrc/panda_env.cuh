@@ -4,6 +4,7 @@
 // panda_gym/envs/robots/panda.py:52-119 (set_action, get_obs), the per-task get_obs / get_achieved_goal /
 // is_success / compute_reward of panda_gym/envs/tasks/<task>.py and panda_gym/utils.py:4-30.
 #pragma once
+#include <string.h>
 #include "panda_contact.cuh"
 
 namespace pg {
@@ -63,8 +64,20 @@ PG_HD double goal_distance(int task, const double* a, const double* b) {
     return d_sqrt(acc);
 }
 // sparse: -(d > thr).astype(float32) -> -1.0 or -0.0;  dense: -d.astype(float32)
-PG_HD float reward_from_distance(int reward_type, float d, float thr) { return reward_type == REWARD_SPARSE ? (d > thr ? -1.0f : -0.0f) : -d; }
-PG_HD float reward_from_distance(int reward_type, double d, double thr) { return reward_type == REWARD_SPARSE ? (d > thr ? -1.0f : -0.0f) : -(float)d; }
+// ptxas 12.9 miscompiles `selp.f32 -1.0, -0.0` into an int->float conversion that yields +0.0, so the sign bit is OR-ed in
+// through an opaque instruction after the {1.0, 0.0} select.
+PG_HD float sparse_reward(bool beyond) {
+#ifdef __CUDA_ARCH__
+    unsigned mag = __float_as_uint(beyond ? 1.0f : 0.0f), bits;
+    asm volatile("or.b32 %0, %1, 0x80000000;" : "=r"(bits) : "r"(mag));
+    return __uint_as_float(bits);
+#else
+    const unsigned bits = beyond ? 0xBF800000u : 0x80000000u;
+    float f; memcpy(&f, &bits, sizeof f); return f;
+#endif
+}
+PG_HD float reward_from_distance(int reward_type, float d, float thr) { return reward_type == REWARD_SPARSE ? sparse_reward(d > thr) : -d; }
+PG_HD float reward_from_distance(int reward_type, double d, double thr) { return reward_type == REWARD_SPARSE ? sparse_reward(d > thr) : -(float)d; }
 
 // pybullet getEulerFromQuaternion
 template <typename T> PG_HD void euler_from_quat(T x, T y, T z, T w, T* e) {
@@ -135,7 +148,7 @@ PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const floa
 // RobotTaskEnv.step for one environment.  q/qd/ob are updated in place.
 template <typename T, int TASK, int CTRL>
 PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action,
-                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C) {
+                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& max_contacts) {
     constexpr int NOBJ = task_nobj(TASK);
     T target[ND], qc[ND];
     env_set_action<T, TASK, CTRL>(M, q, qd, action, target);
@@ -145,6 +158,7 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
         env_substep<T, NOBJ>(M, S, q, qd, target, ob, C);
+        max_contacts = C.n > max_contacts ? C.n : max_contacts;
     }
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
     float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);

@@ -24,6 +24,8 @@ template <typename T> struct EnvDev {
     unsigned* episode;           // [n] episodes started (RNG counter)
     float* ret;                  // [n] running episode return
     double* stats;               // [4] episodes, successes, return sum, length sum
+    int* perm;                   // [n] thread -> env map of the next step (contact-heavy envs first), or NULL
+    unsigned char* ccount;       // [n] largest contact count seen in the env's last step (the sort key)
     Model<T> M;
     Scene<T> S;
 };
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
         store_state<T, NOBJ>(E, i, q, qd, ob);
 #pragma unroll
         for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
-        E.steps[i] = 0; E.episode[i] = ep; E.ret[i] = 0.0f;
+        E.steps[i] = 0; E.episode[i] = ep; E.ret[i] = 0.0f; E.ccount[i] = 0;
         env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
     }
     tile_store<O>((float*)nullptr, io.obs, row0, E.n, obs, false, mine);
@@ -194,25 +196,71 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 }
 
 // ---------------------------------------------------------------------------------------------- step
+// Contact-aware scheduling.  Contact handling is the expensive, data-dependent part of a sub-step; with envs mapped to threads
+// in index order nearly every warp holds a few envs in contact and runs that code at ~10% lane utilisation.  Before each step
+// the envs are therefore stably partitioned by the contact count of their previous step (>= 5, 1..4, 0; heavy first so the long
+// blocks start early), which packs the contact work into full warps.  One block, two passes over per-thread chunks.
+static __global__ void __launch_bounds__(1024) perm_kernel(const unsigned char* __restrict__ ccount, int* __restrict__ perm, int n) {
+    __shared__ int s_cnt[3][1024];
+    __shared__ int s_base[3];
+    const int t = threadIdx.x, chunk = (n + 1023) / 1024, lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int i = lo; i < hi; i++) { int c = ccount[i]; c0 += c >= 5; c1 += (c > 0 && c < 5); c2 += c == 0; }
+    s_cnt[0][t] = c0; s_cnt[1][t] = c1; s_cnt[2][t] = c2;
+    __syncthreads();
+    // exclusive scan of each bucket's per-thread counts (Hillis-Steele over 1024 entries)
+    for (int off = 1; off < 1024; off <<= 1) {
+        int a0 = t >= off ? s_cnt[0][t - off] : 0, a1 = t >= off ? s_cnt[1][t - off] : 0, a2 = t >= off ? s_cnt[2][t - off] : 0;
+        __syncthreads();
+        s_cnt[0][t] += a0; s_cnt[1][t] += a1; s_cnt[2][t] += a2;
+        __syncthreads();
+    }
+    if (t == 0) { s_base[0] = 0; s_base[1] = s_cnt[0][1023]; s_base[2] = s_cnt[0][1023] + s_cnt[1][1023]; }
+    __syncthreads();
+    int p0 = s_base[0] + s_cnt[0][t] - c0, p1 = s_base[1] + s_cnt[1][t] - c1, p2 = s_base[2] + s_cnt[2][t] - c2;
+    for (int i = lo; i < hi; i++) { int c = ccount[i]; if (c >= 5) perm[p0++] = i; else if (c > 0) perm[p1++] = i; else perm[p2++] = i; }
+}
+template <int W, typename E> __device__ __forceinline__ void row_load(const E* g, int i, E* reg) {
+#pragma unroll
+    for (int k = 0; k < W; k++) reg[k] = g[(size_t)i * W + k];
+}
+template <int W, typename E> __device__ __forceinline__ void row_store(E* g, int i, const E* reg) {
+    if (g == nullptr) return;
+#pragma unroll
+    for (int k = 0; k < W; k++) g[(size_t)i * W + k] = reg[k];
+}
+
+// Dynamic shared memory per block: solver_slots() words per thread of solver state (Jx + contact records, word-interleaved), aliased with
+// the I/O row tile that is only live before and after the simulation phase.
+template <typename T, int TASK, int CTRL> constexpr size_t step_smem_bytes() {
+    constexpr int O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
+    constexpr int W = O > NA ? (O > G ? O : G) : (NA > G ? NA : G);
+    constexpr size_t solver = (size_t)solver_slots(task_nobj(TASK)) * BLOCK * sizeof(T), tile = (size_t)W * BLOCK * sizeof(float);
+    return solver > tile ? solver : tile;
+}
 template <typename T, int TASK, int CTRL>
 __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ EnvDev<T> E, const StepIO io) {
     constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
-    constexpr int W = O > NA ? (O > G ? O : G) : (NA > G ? NA : G);   // widest row staged through the tile
-    __shared__ __align__(16) float s_io[BLOCK * W];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float* s_io = reinterpret_cast<float*>(s_raw);
     __shared__ double s_stats[4];
     const long long row0 = (long long)blockIdx.x * BLOCK;
-    const int i = (int)row0 + threadIdx.x;
-    const bool valid = i < E.n;
+    const int t = (int)row0 + threadIdx.x;
+    const bool valid = t < E.n;
+    const bool mapped = E.perm != nullptr;               // block-uniform
+    const int i = (valid && mapped) ? E.perm[t] : t;
     if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
     float act[NA];
-    tile_load<NA>(s_io, io.actions, row0, E.n, act);
+    if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA>(s_io, io.actions, row0, E.n, act);
     float obs[O], ag[G], dg[G], reward = 0.0f;
     unsigned char term = 0, trunc = 0;
     if (valid) {
         T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         Contacts<T> C;
+        C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BLOCK;
         load_state<T, NOBJ>(E, i, q, qd, ob, goal);
-        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, obs, ag, dg, reward, term, C);
+        int max_contacts = 0;
+        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, obs, ag, dg, reward, term, C, max_contacts);
         int steps = E.steps[i] + 1;
         trunc = steps >= task_max_steps(TASK);
         float ret = E.ret[i] + reward;
@@ -222,15 +270,20 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
             env_reset<T, TASK>(E, i, ep, nullptr, nullptr, q, qd, ob, goal);
 #pragma unroll
             for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
-            E.episode[i] = ep; steps = 0; ret = 0.0f;
+            E.episode[i] = ep; steps = 0; ret = 0.0f; max_contacts = 0;
             env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
         }
         store_state<T, NOBJ>(E, i, q, qd, ob);
-        E.steps[i] = steps; E.ret[i] = ret;
+        E.steps[i] = steps; E.ret[i] = ret; E.ccount[i] = (unsigned char)max_contacts;
     }
-    tile_store<O>(s_io, io.obs, row0, E.n, obs, true, valid);
-    tile_store<G>(s_io, io.ag, row0, E.n, ag, true, valid);
-    tile_store<G>(s_io, io.dg, row0, E.n, dg, true, valid);
+    __syncthreads();    // the solver slab is dead for every thread of the block: reuse it as the output tile
+    if (mapped) {
+        if (valid) { row_store<O>(io.obs, i, obs); row_store<G>(io.ag, i, ag); row_store<G>(io.dg, i, dg); }
+    } else {
+        tile_store<O>(s_io, io.obs, row0, E.n, obs, true, valid);
+        tile_store<G>(s_io, io.ag, row0, E.n, ag, true, valid);
+        tile_store<G>(s_io, io.dg, row0, E.n, dg, true, valid);
+    }
     if (valid) {
         if (io.reward) io.reward[i] = reward;
         if (io.terminated) io.terminated[i] = term;

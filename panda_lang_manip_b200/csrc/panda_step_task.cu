@@ -12,8 +12,16 @@ extern long long g_launches;
 
 template <typename T, int TASK> void launch_step(const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st) {
     const int grid = (E.n + BLOCK - 1) / BLOCK;
-    if (ctrl == CTRL_EE) step_kernel<T, TASK, CTRL_EE><<<grid, BLOCK, 0, st>>>(E, io);
-    else step_kernel<T, TASK, CTRL_JOINTS><<<grid, BLOCK, 0, st>>>(E, io);
+    static bool configured = false;
+    if (!configured) {      // > 48 KB of dynamic shared memory needs the opt-in
+        cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_EE>());
+        cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_JOINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_JOINTS>());
+        cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_EE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_JOINTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    if (ctrl == CTRL_EE) step_kernel<T, TASK, CTRL_EE><<<grid, BLOCK, step_smem_bytes<T, TASK, CTRL_EE>(), st>>>(E, io);
+    else step_kernel<T, TASK, CTRL_JOINTS><<<grid, BLOCK, step_smem_bytes<T, TASK, CTRL_JOINTS>(), st>>>(E, io);
     g_launches++;
 }
 template <typename T, int TASK> void launch_reset(const EnvDev<T>& E, const ResetIO& io, cudaStream_t st) {
