@@ -60,6 +60,8 @@ int pg_is_success(int task, const void* achieved_goal, const void* desired_goal,
                   int dtype, void* stream);
 int pg_compute_reward_host(int task, int reward_type, const void* achieved_goal, const void* desired_goal, float* reward,
                            long long m, int dtype, int device);
+int pg_is_success_host(int task, const void* achieved_goal, const void* desired_goal, unsigned char* success, long long m,
+                       int dtype, int device);
 
 /* RobotTaskEnv.save_state / restore_state / remove_state (core.py:252-278; pybullet.py:61-68,266-280): bit-exact device
  * snapshot of the whole batch (state, goals, episode counters). */

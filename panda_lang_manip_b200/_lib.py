@@ -9,7 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpanda_b200.so")
+LIB_PATH = os.environ.get("PANDA_B200_LIB", os.path.join(CSRC, "libpanda_b200.so"))   # override: A/B builds of the same ABI
 
 TASKS = {"reach": 0, "push": 1, "slide": 2, "pick_and_place": 3, "stack": 4, "flip": 5}
 CONTROL = {"ee": 0, "joints": 1}
@@ -18,7 +18,7 @@ PRECISION = {"f32": 0, "f64": 1}
 
 SYMBOLS = [
     "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_host", "pg_compute_reward", "pg_is_success",
-    "pg_compute_reward_host", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
+    "pg_compute_reward_host", "pg_is_success_host", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
@@ -53,6 +53,7 @@ def load() -> ctypes.CDLL:
     lib.pg_compute_reward.argtypes = [c_int, c_int, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_is_success.argtypes = [c_int, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_compute_reward_host.argtypes = [c_int, c_int, vp, vp, vp, c_ll, c_int, c_int]
+    lib.pg_is_success_host.argtypes = [c_int, vp, vp, vp, c_ll, c_int, c_int]
     lib.pg_save_state.argtypes = [vp, pi]
     lib.pg_restore_state.argtypes = [vp, c_int]
     lib.pg_remove_state.argtypes = [vp, c_int]

@@ -245,6 +245,20 @@ int pg_compute_reward_host(int task, int reward_type, const void* ag, const void
     return rc;
 }
 
+int pg_is_success_host(int task, const void* ag, const void* dg, unsigned char* success, long long m, int dtype, int device) {
+    if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success_host: bad argument");
+    if (m == 0) return PG_OK;
+    PG_CUDA(cudaSetDevice(device));
+    const size_t es = dtype == PG_F32 ? 4 : 8, bytes = (size_t)m * task_goal_dim(task) * es;
+    void *da = nullptr, *db = nullptr; unsigned char* dr = nullptr;
+    PG_CUDA(cudaMalloc(&da, bytes)); PG_CUDA(cudaMalloc(&db, bytes)); PG_CUDA(cudaMalloc(&dr, (size_t)m));
+    PG_CUDA(cudaMemcpy(da, ag, bytes, cudaMemcpyHostToDevice)); PG_CUDA(cudaMemcpy(db, dg, bytes, cudaMemcpyHostToDevice));
+    int rc = pg_is_success(task, da, db, dr, m, dtype, nullptr);
+    if (rc == PG_OK) { cudaError_t ce = cudaMemcpy(success, dr, (size_t)m, cudaMemcpyDeviceToHost); if (ce != cudaSuccess) rc = cuda_fail(ce, "cudaMemcpy(success)"); }
+    cudaFree(da); cudaFree(db); cudaFree(dr);
+    return rc;
+}
+
 int pg_save_state(pg_env* e, int* state_id) {
     if (!e || !state_id) return fail(PG_ERR_ARG, "pg_save_state: NULL argument");
     PG_CUDA(cudaSetDevice(e->device));

@@ -229,10 +229,10 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
             for (int a = 0; a < 2; a++) {
                 const int b = 1 - a;
                 for (int k = 0; k < 8; k++) {
-                    V3<T> P = rot_mul(W.Ro[a % NOBJ], obj_vertex(S, a, k)) + ob[a % NOBJ].pos;
-                    V3<T> nl, pl = rot_tmul(W.Ro[b % NOBJ], P - ob[b % NOBJ].pos);
+                    V3<T> P = rot_mul(W.Ro[(NOBJ == 2 ? a : 0)], obj_vertex(S, a, k)) + ob[(NOBJ == 2 ? a : 0)].pos;
+                    V3<T> nl, pl = rot_tmul(W.Ro[(NOBJ == 2 ? b : 0)], P - ob[(NOBJ == 2 ? b : 0)].pos);
                     T d = obj_sdf(S, b, pl, nl);
-                    if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[b % NOBJ], nl), d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
+                    if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[(NOBJ == 2 ? b : 0)], nl), d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
                 }
             }
         }

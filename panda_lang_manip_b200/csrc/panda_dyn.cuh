@@ -476,14 +476,6 @@ template <int D, int SIDE, typename T> PG_HD void limit_row(const T (*Minv)[ND],
     const T sg = SIDE == 0 ? T(1) : T(-1);
     T di = R.lim_rhs[2 * D + SIDE] - sg * dv[D] * R.invD[D];
     T app = R.lim_app[2 * D + SIDE], sum = app + di;
-    // A row resting at zero impulse whose update would stay clamped at zero is an exact no-op; limit rows are in that state almost
-    // always, so the 9-wide velocity update is skipped when no lane of the warp needs it.
-    const bool live = !(app == T(0) && sum <= T(0));
-#ifdef __CUDA_ARCH__
-    if (!__any_sync(__activemask(), live)) return;
-#else
-    if (!live) return;
-#endif
     if (sum < T(0)) { di = -app; sum = T(0); } else if (sum > T(100)) { di = T(100) - app; sum = T(100); }
     R.lim_app[2 * D + SIDE] = sum;
     T w = sg * di;

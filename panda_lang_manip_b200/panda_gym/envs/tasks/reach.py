@@ -1,0 +1,12 @@
+"""Drop-in for reference panda_gym/envs/tasks/reach.py (class Reach): scene, sampling, observation, success and reward of the task are
+implemented by the CUDA kernels (csrc/panda_env.cuh, panda_kernels.cuh env_reset); this class keeps the plug-in interface."""
+from ._base import BuiltinTask
+
+
+class Reach(BuiltinTask):
+    name = "reach"
+    default_threshold = 0.05
+
+    def __init__(self, sim, get_ee_position=None, reward_type="sparse", distance_threshold=None, **kwargs) -> None:
+        self.get_ee_position = get_ee_position
+        super().__init__(sim, reward_type=reward_type, distance_threshold=distance_threshold, **kwargs)
