@@ -168,6 +168,7 @@ struct PoSim {
     double IA[NL][36], U[NL][6], D[NL], u[NL], v[NL][6], c[NL][6], pA[NL][6];
     double Minv[ND][ND];
     Row rows[MAXROWS]; int nrows;
+    double dbg[64][10]; int n_noncontact;   /* per contact: P, n, dist, A-link, B-obj, first row index */
 };
 
 /* ------------------------------------------------------------------ kinematics */
@@ -497,6 +498,9 @@ void po_inverse_kinematics(const PoSim *s, int link, const double pos[3], const 
  * directions from btPlaneSpace1 with the implicit cone clamp, finger links soft (stiffness 30000, damping 1000 ->
  * contact erp/cfm, App. B.3), no warm starting. */
 #define CONTACT_MARGIN 0.004
+/* robot box <-> object: the position-controlled fingers close at up to 5 m/s (10 mm per sub-step), so the speculative margin
+ * of these pairs must exceed that (Bullet's own margin is its 2 cm contact breaking threshold) */
+#define CONTACT_MARGIN_GRASP 0.012
 /* contacts per env and sub-step; later candidates are dropped.  Sized to the solver's on-chip contact store. */
 #define MAXC_ROBOT_ONLY 10
 #define MAXC_OBJECTS 22
@@ -586,6 +590,7 @@ static void add_contact(PoSim *s, const double *gv, const double *P, const doubl
     double t1[3], t2[3]; plane_space(n, t1, t2);
     const double *dirs[3] = {n, t1, t2};
     int nrow = s->nrows;
+    { double *g = s->dbg[s->last_contacts]; v3cpy(g, P); v3cpy(g + 3, n); g[6] = dist; g[7] = linkA >= 0 ? linkA : (linkB >= 0 ? -linkB - 100 : -1); g[8] = objA >= 0 ? objA : (objB >= 0 ? -objB - 100 : -1); g[9] = nrow; }
     double erp = CONTACT_ERP, cfm = 0;
     if (soft) { double k = 30000.0, d = 1000.0; erp = DT * k / (DT * k + d); cfm = 1.0 / (DT * k + d) / DT; }
     for (int k = 0; k < 3; k++) {
@@ -595,7 +600,7 @@ static void add_contact(PoSim *s, const double *gv, const double *P, const doubl
         apply_minv(s, r->J, r->W);
         double den = 0, rel = 0; for (int i = 0; i < NDT; i++) { den += r->J[i] * r->W[i]; rel += r->J[i] * gv[i]; }
         if (k == 0) {
-            r->cfm = cfm; r->invD = 1.0 / (den + cfm);
+            r->invD = 1.0 / (den + cfm); r->cfm = cfm * r->invD;   /* solverConstraint.m_cfm = cfm * m_jacDiagABInv */
             double pen = dist + LINEAR_SLOP, poserr = 0, velerr = -rel;
             if (pen > 0) velerr -= pen / DT; else poserr = -pen * erp / DT;
             r->rhs = (poserr + velerr) * r->invD; r->lo = 0; r->hi = 1e10; r->normal_row = -1;
@@ -633,19 +638,19 @@ static void collect_contacts(PoSim *s, const double *gv) {
     for (int b = 0; b < 3; b++) for (int o = 0; o < s->nobj; o++) {
         const Obj *ob = &s->obj[o]; double R[9], dc[3]; quat_to_R(R, ob->quat);
         v3sub(dc, cb[b], ob->pos);
-        if (v3norm(dc) > v3norm(RBOX[b].h) + v3norm(ob->half) + CONTACT_MARGIN) continue;
+        if (v3norm(dc) > v3norm(RBOX[b].h) + v3norm(ob->half) + CONTACT_MARGIN_GRASP) continue;
         double mu = RBOX[b].mu * ob->mu;
         for (int k = 0; k < 8; k++) { /* robot box vertex in the object's field: A = robot, normal = object's outward */
             double v[3], P[3], pl[3], nl[3], nw[3], t[3]; box_vertex(RBOX[b].h, k, v); m3mulv(P, Rb[b], v); v3add(P, P, cb[b]);
             v3sub(t, P, ob->pos); m3Tmulv(pl, R, t);
             double d = obj_sdf(ob, pl, nl);
-            if (d < CONTACT_MARGIN) { m3mulv(nw, R, nl); add_contact(s, gv, P, nw, d, RBOX[b].link, -1, -1, o, mu, RBOX[b].soft); }
+            if (d < CONTACT_MARGIN_GRASP) { m3mulv(nw, R, nl); add_contact(s, gv, P, nw, d, RBOX[b].link, -1, -1, o, mu, RBOX[b].soft); }
         }
         for (int k = 0; k < 8; k++) { /* object vertex in the robot box's field: A = object */
             double v[3], P[3], pl[3], nl[3], nw[3], t[3]; obj_vertex(ob, k, v); m3mulv(P, R, v); v3add(P, P, ob->pos);
             v3sub(t, P, cb[b]); m3Tmulv(pl, Rb[b], t);
             double d = sdf_box(RBOX[b].h, pl, nl);
-            if (d < CONTACT_MARGIN) { m3mulv(nw, Rb[b], nl); add_contact(s, gv, P, nw, d, -1, o, RBOX[b].link, -1, mu, RBOX[b].soft); }
+            if (d < CONTACT_MARGIN_GRASP) { m3mulv(nw, Rb[b], nl); add_contact(s, gv, P, nw, d, -1, o, RBOX[b].link, -1, mu, RBOX[b].soft); }
         }
     }
     /* 4. object <-> object */
@@ -752,6 +757,12 @@ static void substep(PoSim *s) {
         double n = sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
         for (int k = 0; k < 4; k++) b->quat[k] = nq[k] / n;
     }
+}
+/* debug: contact i of the last sub-step -> P(3) n(3) dist robot-link object normal-impulse friction-impulses(2) */
+int po_get_contact(const PoSim *s, int i, double out[12]) {
+    if (i >= s->last_contacts) return -1;
+    memcpy(out, s->dbg[i], 9 * sizeof(double)); int r = (int)s->dbg[i][9];
+    out[9] = s->rows[r].applied; out[10] = s->rows[r + 1].applied; out[11] = s->rows[r + 2].applied; return 0;
 }
 void po_step(PoSim *s, int n_substeps) { for (int i = 0; i < n_substeps; i++) substep(s); }
 

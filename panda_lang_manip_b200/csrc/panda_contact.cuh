@@ -24,7 +24,7 @@ template <typename T> struct Scene {
     T mass[MAXOBJ], Ic[MAXOBJ][3], mu[MAXOBJ];
     T table_x0, table_x1, table_y0, table_y1;
     T rb_c[3][3], rb_h[3][3], rb_mu[3];   // robot collision boxes: hand (link 8), finger 1, finger 2 -- centre / half extents in the link frame
-    T margin, ground_z, table_mu;
+    T margin, margin_grasp, ground_z, table_mu;   // speculative margins: 4 mm; robot box <-> object 12 mm (fingers close at up to 5 m/s)
     T soft_erp, soft_cfm;       // finger contact stiffness 30000 / damping 1000 -> erp, cfm/dt
 };
 
@@ -203,19 +203,19 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
 #pragma unroll
             for (int o = 0; o < NOBJ; o++) {
                 T orad = sqrt(S.half[o][0] * S.half[o][0] + S.half[o][1] * S.half[o][1] + S.half[o][2] * S.half[o][2]);
-                if (norm(W.cb[b] - ob[o].pos) > rbr + orad + S.margin) continue;
+                if (norm(W.cb[b] - ob[o].pos) > rbr + orad + S.margin_grasp) continue;
                 T mu = S.rb_mu[b] * S.mu[o];
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Rb, box_vertex(S.rb_h[b], k)) + W.cb[b];
                     V3<T> nl, pl = rot_tmul(W.Ro[o], P - ob[o].pos);
                     T d = obj_sdf(S, o, pl, nl);
-                    if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[o], nl), d, b, 3 + o, mu, b > 0);
+                    if (d < S.margin_grasp) add_contact(C, P, rot_mul(W.Ro[o], nl), d, b, 3 + o, mu, b > 0);
                 }
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Ro[o], obj_vertex(S, o, k)) + ob[o].pos;
                     V3<T> nl, pl = rot_tmul(W.Rb, P - W.cb[b]);
                     T d = sdf_box(S.rb_h[b], pl, nl);
-                    if (d < S.margin) add_contact(C, P, rot_mul(W.Rb, nl), d, 3 + o, b, mu, b > 0);
+                    if (d < S.margin_grasp) add_contact(C, P, rot_mul(W.Rb, nl), d, 3 + o, b, mu, b > 0);
                 }
             }
         }
@@ -485,7 +485,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
                 T app = C.f(c, C_APP), inv = C.f(c, C_INVD), di;
                 if (NOBJ == 0 || X.table) {
                     AxisRow<2, 1, T, NOBJ> row(Op, X);
-                    di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm : T(0)) - row.jdv(d8) * inv;
+                    di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - row.jdv(d8) * inv;
                     T sum = app + di;
                     if (sum < T(0)) { di = -app; sum = T(0); }
                     C.f(c, C_APP) = sum;
@@ -494,7 +494,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
                     T w[8];
                     if (X.rb >= 0) robot_wrench<T, NOBJ>(Op, X, X.n, w);
                     T jd = row_jdv<T, NOBJ>(Op, X, X.n, w, d8, dvl, dva, ob);
-                    di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm : T(0)) - jd * inv;
+                    di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - jd * inv;
                     T sum = app + di;
                     if (sum < T(0)) { di = -app; sum = T(0); }
                     C.f(c, C_APP) = sum;

@@ -29,7 +29,7 @@ template <typename T> Scene<T> make_scene(int task) {
     const double rbh[3][3] = {{0.032, 0.102, 0.045}, {0.0105, 0.0105, 0.027}, {0.0105, 0.0105, 0.027}};
     const double rbmu[3] = {0.5, 1.0, 1.0};
     for (int b = 0; b < 3; b++) { for (int k = 0; k < 3; k++) { S.rb_c[b][k] = (T)rbc[b][k]; S.rb_h[b][k] = (T)rbh[b][k]; } S.rb_mu[b] = (T)rbmu[b]; }
-    S.margin = (T)0.004; S.ground_z = (T)-0.4; S.table_mu = (T)0.5;
+    S.margin = (T)0.004; S.margin_grasp = (T)0.012; S.ground_z = (T)-0.4; S.table_mu = (T)0.5;
     const double dt = 1.0 / 500.0, k = 30000.0, d = 1000.0;
     S.soft_erp = (T)(dt * k / (dt * k + d)); S.soft_cfm = (T)(1.0 / (dt * k + d) / dt);
     return S;

@@ -109,9 +109,9 @@ def test_contact_tasks_short_horizon(task):
 
 @pytest.mark.parametrize("task", ["push", "pick_and_place", "stack"])
 def test_contact_tasks_per_step(task):
-    """Per-step (teacher-forced) agreement on contact tasks: robot 1e-4, object pose 1e-4 m."""
+    """Per-step (teacher-forced) agreement on contact tasks: robot 1e-4, object pose (position, quaternion) 5e-4."""
     e = _rollout(task, "ee", n_envs=8, steps=25, precision="f32", seed=4, teacher=True)
-    assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["obj"] < 1e-4, e
+    assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["obj"] < 5e-4 and np.median(e["obj_env"]) < 1e-4, e
 
 
 @pytest.mark.parametrize("task,G", [("reach", 3), ("stack", 6)])
