@@ -500,7 +500,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
                     C.f(c, C_APP) = sum;
                     row_apply<T, NOBJ>(S, W, Op, X, X.n, w, di, d8, F8, dvl, dva, ob);
                 }
-                T r = di / inv; res = fmax(res, r * r);
+                T r = div_fast(di, inv); res = fmax(res, r * r);
             }
             for (int c = 0; c < nc; c++) {          // implicit friction cone over the two tangent rows
                 T napp = C.f(c, C_APP);
@@ -512,7 +512,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
                     AxisRow<1, -1, T, NOBJ> r1(Op, X); AxisRow<0, 1, T, NOBJ> r2(Op, X);
                     T s1 = a1 + C.f(c, C_RHS + 1) - r1.jdv(d8) * i1, s2 = a2 + C.f(c, C_RHS + 2) - r2.jdv(d8) * i2;
                     T len = sqrt(s1 * s1 + s2 * s2);
-                    if (len > lim) { T f = lim / len; s1 *= f; s2 *= f; }
+                    if (len > lim) { T f = div_fast(lim, len); s1 *= f; s2 *= f; }
                     d1 = s1 - a1; d2 = s2 - a2;
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
                     r1.apply(Op, d1, d8, F8); r2.apply(Op, d2, d8, F8);
@@ -523,13 +523,13 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
                     T j1 = row_jdv<T, NOBJ>(Op, X, t1, w1, d8, dvl, dva, ob), j2 = row_jdv<T, NOBJ>(Op, X, t2, w2, d8, dvl, dva, ob);
                     T s1 = a1 + C.f(c, C_RHS + 1) - j1 * i1, s2 = a2 + C.f(c, C_RHS + 2) - j2 * i2;
                     T len = sqrt(s1 * s1 + s2 * s2);
-                    if (len > lim) { T f = lim / len; s1 *= f; s2 *= f; }
+                    if (len > lim) { T f = div_fast(lim, len); s1 *= f; s2 *= f; }
                     d1 = s1 - a1; d2 = s2 - a2;
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
                     row_apply<T, NOBJ>(S, W, Op, X, t1, w1, d1, d8, F8, dvl, dva, ob);
                     row_apply<T, NOBJ>(S, W, Op, X, t2, w2, d2, d8, F8, dvl, dva, ob);
                 }
-                T r1 = d1 / i1, r2 = d2 / i2;
+                T r1 = div_fast(d1, i1), r2 = div_fast(d2, i2);
                 res = fmax(res, fmax(r1 * r1, r2 * r2));
             }
             if (robot_contacts) {       // fold this sweep's contact wrench back into the joint velocities: dvq += M^-1 Jx^T F8

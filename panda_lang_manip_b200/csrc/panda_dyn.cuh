@@ -69,6 +69,16 @@ PG_HD void sincos_t(float a, float& s, float& c) {
 #endif
 }
 PG_HD void sincos_t(double a, double& s, double& c) { s = sin(a); c = cos(a); }
+// quotient for the solver's convergence metric and cone scaling: the IEEE float division expands to a guarded sequence whose slow
+// path is taken for zero numerators (the common case of an inactive row); the approximate form is one MUFU.RCP + multiply
+PG_HD float div_fast(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+PG_HD double div_fast(double a, double b) { return a / b; }
 
 // constant part of the arm joint frames: roll about x by ROLL * 90 deg
 PG_HD constexpr int roll_of(int i) { return i == 0 ? 0 : ((i == 1 || i == 4) ? -1 : 1); }
