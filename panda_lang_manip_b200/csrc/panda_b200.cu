@@ -170,7 +170,7 @@ int pg_step(pg_env* e, const float* actions, float* obs, float* ag, float* dg, f
     // contact-aware thread -> env map (see perm_kernel); small batches keep the identity map and the tiled I/O path
     int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
     const bool use_perm = e->sort_envs && e->n >= 4096;
-    if (use_perm) { perm_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, perm, e->n); g_launches++; }
+    if (use_perm) { perm_kernel<<<1, PERM_THREADS, 0, (cudaStream_t)stream>>>(e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, perm, e->n); g_launches++; }
     EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
     if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
     if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, (cudaStream_t)stream);

@@ -198,27 +198,43 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 // ---------------------------------------------------------------------------------------------- step
 // Contact-aware scheduling.  Contact handling is the expensive, data-dependent part of a sub-step; with envs mapped to threads
 // in index order nearly every warp holds a few envs in contact and runs that code at ~10% lane utilisation.  Before each step
-// the envs are therefore stably partitioned by the contact count of their previous step (>= 5, 1..4, 0; heavy first so the long
-// blocks start early), which packs the contact work into full warps.  One block, two passes over per-thread chunks.
-static __global__ void __launch_bounds__(1024) perm_kernel(const unsigned char* __restrict__ ccount, int* __restrict__ perm, int n) {
-    __shared__ int s_cnt[3][1024];
-    __shared__ int s_base[3];
-    const int t = threadIdx.x, chunk = (n + 1023) / 1024, lo = min(n, t * chunk), hi = min(n, lo + chunk);
-    int c0 = 0, c1 = 0, c2 = 0;
-    for (int i = lo; i < hi; i++) { int c = ccount[i]; c0 += c >= 5; c1 += (c > 0 && c < 5); c2 += c == 0; }
-    s_cnt[0][t] = c0; s_cnt[1][t] = c1; s_cnt[2][t] = c2;
+// the envs are therefore stably bucket-sorted by the contact count of their previous step (heaviest first so the long blocks
+// start early), which packs the contact work into full warps.  One block, two passes over per-thread chunks.
+constexpr int PERM_THREADS = 512, PERM_BUCKETS = 12;   // bucket = min(contact count, 11); heaviest first
+static __global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const unsigned char* __restrict__ ccount, int* __restrict__ perm, int n) {
+    __shared__ int s_cnt[PERM_BUCKETS][PERM_THREADS];
+    __shared__ int s_base[PERM_BUCKETS];
+    const int t = threadIdx.x, chunk = (n + PERM_THREADS - 1) / PERM_THREADS, lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    int cnt[PERM_BUCKETS];
+#pragma unroll
+    for (int b = 0; b < PERM_BUCKETS; b++) cnt[b] = 0;
+    for (int i = lo; i < hi; i++) {
+        int c = min((int)ccount[i], PERM_BUCKETS - 1);
+#pragma unroll
+        for (int b = 0; b < PERM_BUCKETS; b++) cnt[b] += (c == b);
+    }
+#pragma unroll
+    for (int b = 0; b < PERM_BUCKETS; b++) s_cnt[b][t] = cnt[b];
     __syncthreads();
-    // exclusive scan of each bucket's per-thread counts (Hillis-Steele over 1024 entries)
-    for (int off = 1; off < 1024; off <<= 1) {
-        int a0 = t >= off ? s_cnt[0][t - off] : 0, a1 = t >= off ? s_cnt[1][t - off] : 0, a2 = t >= off ? s_cnt[2][t - off] : 0;
+    for (int off = 1; off < PERM_THREADS; off <<= 1) {     // inclusive scan of every bucket's per-thread counts
+        int add[PERM_BUCKETS];
+#pragma unroll
+        for (int b = 0; b < PERM_BUCKETS; b++) add[b] = t >= off ? s_cnt[b][t - off] : 0;
         __syncthreads();
-        s_cnt[0][t] += a0; s_cnt[1][t] += a1; s_cnt[2][t] += a2;
+#pragma unroll
+        for (int b = 0; b < PERM_BUCKETS; b++) s_cnt[b][t] += add[b];
         __syncthreads();
     }
-    if (t == 0) { s_base[0] = 0; s_base[1] = s_cnt[0][1023]; s_base[2] = s_cnt[0][1023] + s_cnt[1][1023]; }
+    if (t == 0) { int acc = 0; for (int b = PERM_BUCKETS - 1; b >= 0; b--) { s_base[b] = acc; acc += s_cnt[b][PERM_THREADS - 1]; } }
     __syncthreads();
-    int p0 = s_base[0] + s_cnt[0][t] - c0, p1 = s_base[1] + s_cnt[1][t] - c1, p2 = s_base[2] + s_cnt[2][t] - c2;
-    for (int i = lo; i < hi; i++) { int c = ccount[i]; if (c >= 5) perm[p0++] = i; else if (c > 0) perm[p1++] = i; else perm[p2++] = i; }
+    int pos[PERM_BUCKETS];
+#pragma unroll
+    for (int b = 0; b < PERM_BUCKETS; b++) pos[b] = s_base[b] + s_cnt[b][t] - cnt[b];
+    for (int i = lo; i < hi; i++) {
+        int c = min((int)ccount[i], PERM_BUCKETS - 1);
+#pragma unroll
+        for (int b = 0; b < PERM_BUCKETS; b++) if (c == b) perm[pos[b]++] = i;
+    }
 }
 template <int W, typename E> __device__ __forceinline__ void row_load(const E* g, int i, E* reg) {
 #pragma unroll
