@@ -133,6 +133,7 @@ template <typename T> struct CStore {   // per-thread view of the shared-memory 
 template <typename T> struct Contacts {
     CStore<T> st;
     int n, nr, cap;
+    bool near;                  // the gripper is within 3 cm of the table or inside an object's broad-phase sphere (scheduling hint)
     PG_HD T& f(int c, int k) { return st.at(JX_SLOTS + c * REC + k); }
     PG_HD T& jx(int j, int a) { return st.at(6 * j + a); }
 };
@@ -171,7 +172,7 @@ template <typename T> PG_HD bool over_table(const Scene<T>& S, V3<T> p) { return
 
 template <typename T, int NOBJ>
 PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Obj<T>* ob, Contacts<T>& C) {
-    C.n = 0; C.nr = 0; C.cap = max_contacts(NOBJ);
+    C.n = 0; C.nr = 0; C.cap = max_contacts(NOBJ); C.near = false;
     const V3<T> up = mk<T>(T(0), T(0), T(1));
     // 1. object vertices against the table top / ground plane
 #pragma unroll
@@ -187,6 +188,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
 #pragma unroll
     for (int b = 0; b < 3; b++) {
         T lowest = W.cb[b].z - (fabs(W.Rb.X.z) * S.rb_h[b][0] + fabs(W.Rb.Y.z) * S.rb_h[b][1] + fabs(W.Rb.Z.z) * S.rb_h[b][2]);
+        C.near = C.near || lowest < T(0.03);
         if (lowest >= S.margin) continue;
         for (int k = 0; k < 8; k++) {
             // fingers: outer-face vertices only (against a plane the inner-face vertices of the pair are never the lowest points)
@@ -204,6 +206,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
             for (int o = 0; o < NOBJ; o++) {
                 T orad = sqrt(S.half[o][0] * S.half[o][0] + S.half[o][1] * S.half[o][1] + S.half[o][2] * S.half[o][2]);
                 if (norm(W.cb[b] - ob[o].pos) > rbr + orad + S.margin_grasp) continue;
+                C.near = true;
                 T mu = S.rb_mu[b] * S.mu[o];
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Rb, box_vertex(S.rb_h[b], k)) + W.cb[b];

@@ -158,7 +158,8 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
         env_substep<T, NOBJ>(M, S, q, qd, target, ob, C);
-        max_contacts = C.n > max_contacts ? C.n : max_contacts;
+        if (C.n > (max_contacts & 0x7f)) max_contacts = C.n | (max_contacts & 0x80);   // low 7 bits: largest contact count of the step
+        if (C.near) max_contacts |= 0x80;     // scheduling hint bit: close to a contact
     }
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
     float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 // in index order nearly every warp holds a few envs in contact and runs that code at ~10% lane utilisation.  Before each step
 // the envs are therefore stably bucket-sorted by the contact count of their previous step (heaviest first so the long blocks
 // start early), which packs the contact work into full warps.  One block, two passes over per-thread chunks.
-constexpr int PERM_THREADS = 512, PERM_BUCKETS = 12;   // bucket = min(contact count, 11); heaviest first
+constexpr int PERM_THREADS = 512, PERM_BUCKETS = 12;   // bucket: 0 far from any contact, 1 near one, 1 + min(contact count, 10); heaviest first
+__device__ __forceinline__ int perm_bucket(unsigned char key) { int c = key & 0x7f; return c > 0 ? 1 + min(c, PERM_BUCKETS - 2) : (key >> 7); }
 static __global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const unsigned char* __restrict__ ccount, int* __restrict__ perm, int n) {
     __shared__ int s_cnt[PERM_BUCKETS][PERM_THREADS];
     __shared__ int s_base[PERM_BUCKETS];
@@ -209,7 +210,7 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const unsigne
 #pragma unroll
     for (int b = 0; b < PERM_BUCKETS; b++) cnt[b] = 0;
     for (int i = lo; i < hi; i++) {
-        int c = min((int)ccount[i], PERM_BUCKETS - 1);
+        int c = perm_bucket(ccount[i]);
 #pragma unroll
         for (int b = 0; b < PERM_BUCKETS; b++) cnt[b] += (c == b);
     }
@@ -231,7 +232,7 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const unsigne
 #pragma unroll
     for (int b = 0; b < PERM_BUCKETS; b++) pos[b] = s_base[b] + s_cnt[b][t] - cnt[b];
     for (int i = lo; i < hi; i++) {
-        int c = min((int)ccount[i], PERM_BUCKETS - 1);
+        int c = perm_bucket(ccount[i]);
 #pragma unroll
         for (int b = 0; b < PERM_BUCKETS; b++) if (c == b) perm[pos[b]++] = i;
     }
