@@ -500,10 +500,10 @@ void po_inverse_kinematics(const PoSim *s, int link, const double pos[3], const 
 #define CONTACT_MARGIN 0.004
 /* robot box <-> object: the position-controlled fingers close at up to 5 m/s (10 mm per sub-step), so the speculative margin
  * of these pairs must exceed that (Bullet's own margin is its 2 cm contact breaking threshold) */
-#define CONTACT_MARGIN_GRASP 0.012
+#define CONTACT_MARGIN_GRASP 0.012   /* applies when the closest feature is a face; edge / corner configurations use CONTACT_MARGIN */
 /* contacts per env and sub-step; later candidates are dropped.  Sized to the solver's on-chip contact store. */
-#define MAXC_ROBOT_ONLY 10
-#define MAXC_OBJECTS 22
+#define MAXC_ONE_OBJECT 10   /* no object or one */
+#define MAXC_TWO_OBJECTS 22
 #define CONTACT_ERP 0.2
 #define LINEAR_SLOP 1e-5
 #define GROUND_Z (-0.4)
@@ -524,13 +524,16 @@ static void obj_vertex(const Obj *b, int k, double *o) {
     else { double ang = PI / 4 + (k & 3) * (PI / 2); v3set(o, b->half[0] * cos(ang), b->half[0] * sin(ang), (k & 4) ? b->half[2] : -b->half[2]); }
 }
 /* signed distance of local point p to a box of half extents h; n = outward normal (local) */
+static int g_face; /* set by the sdf functions: 1 when the closest feature is a face (or the point is inside) */
 static double sdf_box(const double *h, const double *p, double *n) {
+    g_face = 1;
     double d[3] = {fabs(p[0]) - h[0], fabs(p[1]) - h[1], fabs(p[2]) - h[2]};
     if (d[0] <= 0 && d[1] <= 0 && d[2] <= 0) { /* inside: nearest face */
         int a = 0; if (d[1] > d[a]) a = 1; if (d[2] > d[a]) a = 2;
         v3set(n, 0, 0, 0); n[a] = p[a] >= 0 ? 1 : -1; return d[a];
     }
     double o[3] = {d[0] > 0 ? d[0] : 0, d[1] > 0 ? d[1] : 0, d[2] > 0 ? d[2] : 0};
+    g_face = ((d[0] > 0) + (d[1] > 0) + (d[2] > 0)) == 1;
     double len = v3norm(o);
     for (int k = 0; k < 3; k++) n[k] = (p[k] >= 0 ? o[k] : -o[k]) / len;
     return len;
@@ -540,6 +543,7 @@ static double sdf_cyl(double r, double hz, const double *p, double *n) {
     double rho = sqrt(p[0] * p[0] + p[1] * p[1]);
     double dr = rho - r, dz = fabs(p[2]) - hz;
     double rx = rho > 1e-12 ? p[0] / rho : 1, ry = rho > 1e-12 ? p[1] / rho : 0, sz = p[2] >= 0 ? 1 : -1;
+    g_face = !(dr > 0 && dz > 0);
     if (dr <= 0 && dz <= 0) { if (dr > dz) { v3set(n, rx, ry, 0); return dr; } v3set(n, 0, 0, sz); return dz; }
     double a = dr > 0 ? dr : 0, b = dz > 0 ? dz : 0, len = sqrt(a * a + b * b);
     v3set(n, rx * a / len, ry * a / len, sz * b / len);
@@ -585,7 +589,7 @@ static void plane_space(const double *n, double *p, double *q) { /* btPlaneSpace
 /* one contact: point P (world), normal n (world, pointing from B to A), distance; A/B are (link,obj) with -1/-1 = static */
 static void add_contact(PoSim *s, const double *gv, const double *P, const double *n, double dist, int linkA, int objA, int linkB, int objB, double mu, int soft) {
     int on_robot = linkA >= 0 || linkB >= 0;
-    if (s->last_contacts >= (s->nobj == 0 ? MAXC_ROBOT_ONLY : MAXC_OBJECTS)) return;
+    if (s->last_contacts >= (s->nobj <= 1 ? MAXC_ONE_OBJECT : MAXC_TWO_OBJECTS)) return;
     if (on_robot) s->last_robot_contacts++;
     double t1[3], t2[3]; plane_space(n, t1, t2);
     const double *dirs[3] = {n, t1, t2};
@@ -644,13 +648,13 @@ static void collect_contacts(PoSim *s, const double *gv) {
             double v[3], P[3], pl[3], nl[3], nw[3], t[3]; box_vertex(RBOX[b].h, k, v); m3mulv(P, Rb[b], v); v3add(P, P, cb[b]);
             v3sub(t, P, ob->pos); m3Tmulv(pl, R, t);
             double d = obj_sdf(ob, pl, nl);
-            if (d < CONTACT_MARGIN_GRASP) { m3mulv(nw, R, nl); add_contact(s, gv, P, nw, d, RBOX[b].link, -1, -1, o, mu, RBOX[b].soft); }
+            if (d < CONTACT_MARGIN || (d < CONTACT_MARGIN_GRASP && g_face)) { m3mulv(nw, R, nl); add_contact(s, gv, P, nw, d, RBOX[b].link, -1, -1, o, mu, RBOX[b].soft); }
         }
         for (int k = 0; k < 8; k++) { /* object vertex in the robot box's field: A = object */
             double v[3], P[3], pl[3], nl[3], nw[3], t[3]; obj_vertex(ob, k, v); m3mulv(P, R, v); v3add(P, P, ob->pos);
             v3sub(t, P, cb[b]); m3Tmulv(pl, Rb[b], t);
             double d = sdf_box(RBOX[b].h, pl, nl);
-            if (d < CONTACT_MARGIN_GRASP) { m3mulv(nw, Rb[b], nl); add_contact(s, gv, P, nw, d, -1, o, RBOX[b].link, -1, mu, RBOX[b].soft); }
+            if (d < CONTACT_MARGIN || (d < CONTACT_MARGIN_GRASP && g_face)) { m3mulv(nw, Rb[b], nl); add_contact(s, gv, P, nw, d, -1, o, RBOX[b].link, -1, mu, RBOX[b].soft); }
         }
     }
     /* 4. object <-> object */

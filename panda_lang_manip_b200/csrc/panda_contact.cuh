@@ -24,7 +24,7 @@ template <typename T> struct Scene {
     T mass[MAXOBJ], Ic[MAXOBJ][3], mu[MAXOBJ];
     T table_x0, table_x1, table_y0, table_y1;
     T rb_c[3][3], rb_h[3][3], rb_mu[3];   // robot collision boxes: hand (link 8), finger 1, finger 2 -- centre / half extents in the link frame
-    T margin, margin_grasp, ground_z, table_mu;   // speculative margins: 4 mm; robot box <-> object 12 mm (fingers close at up to 5 m/s)
+    T margin, margin_grasp, ground_z, table_mu;   // speculative margins: 4 mm; robot box <-> object 12 mm when the closest feature is a face (fingers close at up to 5 m/s)
     T soft_erp, soft_cfm;       // finger contact stiffness 30000 / damping 1000 -> erp, cfm/dt
 };
 
@@ -74,7 +74,8 @@ template <typename T> PG_HD V3<T> obj_vertex(const Scene<T>& S, int o, int k) {
     int a = k & 3;
     return mk<T>((a == 0 || a == 3) ? c : -c, (a < 2) ? c : -c, (k & 4) ? S.half[o][2] : -S.half[o][2]);
 }
-template <typename T> PG_HD T sdf_box(const T* h, V3<T> p, V3<T>& n) {
+template <typename T> PG_HD T sdf_box(const T* h, V3<T> p, V3<T>& n, bool& face) {
+    face = true;
     T dx = fabs(p.x) - h[0], dy = fabs(p.y) - h[1], dz = fabs(p.z) - h[2];
     if (dx <= 0 && dy <= 0 && dz <= 0) {
         int a = 0; T d = dx;
@@ -85,21 +86,23 @@ template <typename T> PG_HD T sdf_box(const T* h, V3<T> p, V3<T>& n) {
         return d;
     }
     T ox = dx > 0 ? dx : T(0), oy = dy > 0 ? dy : T(0), oz = dz > 0 ? dz : T(0);
+    face = ((dx > 0) + (dy > 0) + (dz > 0)) == 1;
     T len = sqrt(ox * ox + oy * oy + oz * oz), inv = T(1) / len;
     n = mk<T>((p.x >= 0 ? ox : -ox) * inv, (p.y >= 0 ? oy : -oy) * inv, (p.z >= 0 ? oz : -oz) * inv);
     return len;
 }
-template <typename T> PG_HD T sdf_cyl(T r, T hz, V3<T> p, V3<T>& n) {
+template <typename T> PG_HD T sdf_cyl(T r, T hz, V3<T> p, V3<T>& n, bool& face) {
     T rho = sqrt(p.x * p.x + p.y * p.y);
     T dr = rho - r, dz = fabs(p.z) - hz;
     T rx = rho > T(1e-12) ? p.x / rho : T(1), ry = rho > T(1e-12) ? p.y / rho : T(0), sz = p.z >= 0 ? T(1) : T(-1);
+    face = !(dr > 0 && dz > 0);
     if (dr <= 0 && dz <= 0) { if (dr > dz) { n = mk<T>(rx, ry, T(0)); return dr; } n = mk<T>(T(0), T(0), sz); return dz; }
     T a = dr > 0 ? dr : T(0), b = dz > 0 ? dz : T(0), len = sqrt(a * a + b * b);
     n = mk<T>(rx * a / len, ry * a / len, sz * b / len);
     return len;
 }
-template <typename T> PG_HD T obj_sdf(const Scene<T>& S, int o, V3<T> p, V3<T>& n) {
-    return S.shape[o] == SH_BOX ? sdf_box(S.half[o], p, n) : sdf_cyl(S.half[o][0], S.half[o][2], p, n);
+template <typename T> PG_HD T obj_sdf(const Scene<T>& S, int o, V3<T> p, V3<T>& n, bool& face) {
+    return S.shape[o] == SH_BOX ? sdf_box(S.half[o], p, n, face) : sdf_cyl(S.half[o][0], S.half[o][2], p, n, face);
 }
 template <typename T> PG_HD void plane_space(V3<T> n, V3<T>& p, V3<T>& q) {   // btPlaneSpace1
     if (fabs(n.z) > Consts<T>::k45) {
@@ -122,7 +125,7 @@ constexpr int REC = 17;                 // words per contact record
 constexpr int JX_SLOTS = 42;            // Jx: per arm joint j, angular (z_j) and linear (z_j x (O6 - p_j)) columns
 // contacts per env and sub-step (later candidates are dropped; the oracle applies the same cap): robot-only scenes keep two
 // 128-thread blocks per SM, scenes with objects take the whole SM's shared memory for one block
-PG_HD constexpr int max_contacts(int nobj) { return nobj == 0 ? 10 : 22; }
+PG_HD constexpr int max_contacts(int nobj) { return nobj <= 1 ? 10 : 22; }
 PG_HD constexpr int solver_slots(int nobj) { return JX_SLOTS + max_contacts(nobj) * REC; }
 enum { C_P = 0, C_N = 3, C_INVD = 6, C_RHS = 9, C_APP = 12, C_MU = 15, C_CODE = 16 };
 
@@ -181,7 +184,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
             V3<T> P = rot_mul(W.Ro[o], obj_vertex(S, o, k)) + ob[o].pos;
             T plane = (over_table(S, P) && P.z > T(-0.05)) ? T(0) : S.ground_z;
             T d = P.z - plane;
-            if (d < S.margin) add_contact(C, P, up, d, 3 + o, -1, S.mu[o] * S.table_mu, false);
+            if (d < S.margin) add_contact(C, P, up, d, 3 + o, -1, S.mu[o] * S.table_mu, false, true);
         }
     }
     // 2. robot box vertices against the table top
@@ -211,14 +214,14 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Rb, box_vertex(S.rb_h[b], k)) + W.cb[b];
                     V3<T> nl, pl = rot_tmul(W.Ro[o], P - ob[o].pos);
-                    T d = obj_sdf(S, o, pl, nl);
-                    if (d < S.margin_grasp) add_contact(C, P, rot_mul(W.Ro[o], nl), d, b, 3 + o, mu, b > 0);
+                    bool face; T d = obj_sdf(S, o, pl, nl, face);
+                    if (d < S.margin || (d < S.margin_grasp && face)) add_contact(C, P, rot_mul(W.Ro[o], nl), d, b, 3 + o, mu, b > 0);
                 }
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Ro[o], obj_vertex(S, o, k)) + ob[o].pos;
                     V3<T> nl, pl = rot_tmul(W.Rb, P - W.cb[b]);
-                    T d = sdf_box(S.rb_h[b], pl, nl);
-                    if (d < S.margin_grasp) add_contact(C, P, rot_mul(W.Rb, nl), d, 3 + o, b, mu, b > 0);
+                    bool face; T d = sdf_box(S.rb_h[b], pl, nl, face);
+                    if (d < S.margin || (d < S.margin_grasp && face)) add_contact(C, P, rot_mul(W.Rb, nl), d, 3 + o, b, mu, b > 0);
                 }
             }
         }
@@ -234,7 +237,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Ro[(NOBJ == 2 ? a : 0)], obj_vertex(S, a, k)) + ob[(NOBJ == 2 ? a : 0)].pos;
                     V3<T> nl, pl = rot_tmul(W.Ro[(NOBJ == 2 ? b : 0)], P - ob[(NOBJ == 2 ? b : 0)].pos);
-                    T d = obj_sdf(S, b, pl, nl);
+                    bool face; T d = obj_sdf(S, b, pl, nl, face);
                     if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[(NOBJ == 2 ? b : 0)], nl), d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
                 }
             }
@@ -341,6 +344,24 @@ template <int AX, int SG, typename T, int NOBJ> struct AxisRow {
     }
     PG_HD T den(const OpSpace<T>& Op) const { T y[8]; lam(Op, y); return jdv(y); }
 };
+// Object-vs-plane row along SG * e_AX (the object is body A): J = [e; r x e], W = [e/m; Iinv (r x e)] with r x e_AX two-sparse.
+template <int AX, int SG, typename T> struct ObjAxisRow {
+    static constexpr int I1 = (AX + 1) % 3, I2 = (AX + 2) % 3;
+    T m1, m2;
+    PG_HD ObjAxisRow(V3<T> r) { const T rr[3] = {r.x, r.y, r.z}; m1 = T(SG) * rr[I2]; m2 = T(-SG) * rr[I1]; }
+    PG_HD T jdv(V3<T> vl, V3<T> va) const { const T l[3] = {vl.x, vl.y, vl.z}, a[3] = {va.x, va.y, va.z}; return T(SG) * l[AX] + m1 * a[I1] + m2 * a[I2]; }
+    PG_HD V3<T> wang(const T* I) const {        // Iinv (r x e): columns I1, I2 of the symmetric matrix
+        const int c1[3] = {I1 == 0 ? 0 : (I1 == 1 ? 1 : 2), I1 == 0 ? 1 : (I1 == 1 ? 3 : 4), I1 == 0 ? 2 : (I1 == 1 ? 4 : 5)};
+        const int c2[3] = {I2 == 0 ? 0 : (I2 == 1 ? 1 : 2), I2 == 0 ? 1 : (I2 == 1 ? 3 : 4), I2 == 0 ? 2 : (I2 == 1 ? 4 : 5)};
+        return mk<T>(I[c1[0]] * m1 + I[c2[0]] * m2, I[c1[1]] * m1 + I[c2[1]] * m2, I[c1[2]] * m1 + I[c2[2]] * m2);
+    }
+    PG_HD T den(const T* I, T inv_mass) const { V3<T> w = wang(I); const T a[3] = {w.x, w.y, w.z}; return inv_mass + m1 * a[I1] + m2 * a[I2]; }
+    PG_HD void apply(const T* I, T inv_mass, T di, V3<T>& vl, V3<T>& va) const {
+        const T dl = T(SG) * di * inv_mass;
+        if (AX == 0) vl.x += dl; else if (AX == 1) vl.y += dl; else vl.z += dl;
+        va = va + wang(I) * di;
+    }
+};
 template <typename T> PG_HD T dot8(const T* a, const T* b) {
     T t = T(0);
 #pragma unroll
@@ -360,7 +381,7 @@ PG_HD void rows_setup(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<
         for (int k = 0; k < 3; k++) {
             V3<T> d = k == 0 ? X.n : (k == 1 ? t1 : t2);
             T den = T(0), rel = T(0);
-            if (NOBJ == 0 || X.table) {
+            if (NOBJ == 0 || (X.table && X.rb >= 0)) {
                 if (k == 0) { AxisRow<2, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
                 else if (k == 1) { AxisRow<1, -1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
                 else { AxisRow<0, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
@@ -486,13 +507,21 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
             for (int c = 0; c < nc; c++) {          // contact normals
                 ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
                 T app = C.f(c, C_APP), inv = C.f(c, C_INVD), di;
-                if (NOBJ == 0 || X.table) {
+                if (NOBJ == 0 || (X.table && X.rb >= 0)) {
                     AxisRow<2, 1, T, NOBJ> row(Op, X);
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - row.jdv(d8) * inv;
                     T sum = app + di;
                     if (sum < T(0)) { di = -app; sum = T(0); }
                     C.f(c, C_APP) = sum;
                     row.apply(Op, di, d8, F8);
+                } else if (X.table) {       // object vertex on the table / ground plane
+                    const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
+                    ObjAxisRow<2, 1, T> row(X.P - ob[o].pos);
+                    di = C.f(c, C_RHS) - row.jdv(dvl[o], dva[o]) * inv;
+                    T sum = app + di;
+                    if (sum < T(0)) { di = -app; sum = T(0); }
+                    C.f(c, C_APP) = sum;
+                    row.apply(W.Iinv[o], T(1) / S.mass[o], di, dvl[o], dva[o]);
                 } else {
                     T w[8];
                     if (X.rb >= 0) robot_wrench<T, NOBJ>(Op, X, X.n, w);
@@ -511,7 +540,18 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
                 ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
                 T a1 = C.f(c, C_APP + 1), a2 = C.f(c, C_APP + 2), i1 = C.f(c, C_INVD + 1), i2 = C.f(c, C_INVD + 2);
                 T lim = C.f(c, C_MU) * napp, d1, d2;
-                if (NOBJ == 0 || X.table) {
+                if (NOBJ > 0 && X.table && X.rb < 0) {
+                    const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
+                    V3<T> r = X.P - ob[o].pos;
+                    ObjAxisRow<1, -1, T> r1(r); ObjAxisRow<0, 1, T> r2(r);
+                    T s1 = a1 + C.f(c, C_RHS + 1) - r1.jdv(dvl[o], dva[o]) * i1, s2 = a2 + C.f(c, C_RHS + 2) - r2.jdv(dvl[o], dva[o]) * i2;
+                    T len = sqrt(s1 * s1 + s2 * s2);
+                    if (len > lim) { T f = div_fast(lim, len); s1 *= f; s2 *= f; }
+                    d1 = s1 - a1; d2 = s2 - a2;
+                    C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
+                    const T im = T(1) / S.mass[o];
+                    r1.apply(W.Iinv[o], im, d1, dvl[o], dva[o]); r2.apply(W.Iinv[o], im, d2, dvl[o], dva[o]);
+                } else if (NOBJ == 0 || X.table) {
                     AxisRow<1, -1, T, NOBJ> r1(Op, X); AxisRow<0, 1, T, NOBJ> r2(Op, X);
                     T s1 = a1 + C.f(c, C_RHS + 1) - r1.jdv(d8) * i1, s2 = a2 + C.f(c, C_RHS + 2) - r2.jdv(d8) * i2;
                     T len = sqrt(s1 * s1 + s2 * s2);
