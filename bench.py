@@ -202,6 +202,24 @@ def run_gpu(args):
     h2d = n * A * 4
     d2h = n * (OBS[args.task] + 2 * GOAL[args.task] + 1) * 4 + 2 * n
 
+    # HER relabelling kernel (the one genuinely HBM-bound kernel of the path): compute_reward on M transitions
+    her = None
+    if rank == 0 and not args.no_her:
+        her = {}
+        for name, task, G, M in (("stack_1M_rows_6d (BASELINE configs[4], L2-resident)", "stack", 6, 1 << 20), ("reach_32M_rows_3d (HBM-resident)", "reach", 3, 1 << 25)):
+            ag = torch.rand((M, G), device=dev); dg = torch.rand((M, G), device=dev)
+            for _ in range(3):
+                p.compute_reward(task, "sparse", ag, dg)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for a, b in evs:
+                if M < (1 << 24):
+                    flush.zero_()
+                a.record(); p.compute_reward(task, "sparse", ag, dg); b.record()
+            torch.cuda.synchronize(dev)
+            ms = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+            nbytes = M * (2 * G * 4 + 4)
+            her[name] = {"transitions_per_s": M / (ms / 1e3), "ms": ms, "achieved_gbs": nbytes / (ms / 1e3) / 1e9, "bytes_per_transition": 2 * G * 4 + 4}
+            del ag, dg
     if rank == 0:
         peaks = {}
         try:
@@ -222,11 +240,15 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "step_kernel", "bytes_per_env_step": bps, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "latency/issue-bound kernel (~1 MFLOP of serial dynamics per env-step): the HBM fraction is structurally tiny, see DESIGN.md"},
+            "her_compute_reward": her,
             "clocks": clocks,
             "wall_s_timed_loop": t_wall,
             "episode_stats": {"episodes": stats[0].item(), "success_rate": (stats[1] / stats[0]).item() if stats[0].item() > 0 else None,
                               "mean_return": (stats[2] / stats[0]).item() if stats[0].item() > 0 else None},
         }
+        if her:
+            for v in her.values():
+                v["frac_of_measured_hbm"] = v["achieved_gbs"] / peak
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             lib = oracle_lib()
@@ -253,6 +275,7 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-her", action="store_true", help="skip the HER compute_reward measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -88,12 +88,13 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
 }
 
 template <typename E, bool WANT_REWARD> static void launch_reward(int task, const E* ag, const E* dg, float* reward, unsigned char* success, long long m, int reward_type, cudaStream_t st) {
-    long long blocks = (m + BLOCK - 1) / BLOCK;
-    int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);   // persistent-style grid: a multiple of the SM count, rows strided
+    const int vec_ok = (((uintptr_t)ag | (uintptr_t)dg) & 15) == 0;
+    long long blocks = (m / 2 + 255) / 256 + 1;
+    int grid = (int)(blocks < 148LL * 32 ? blocks : 148LL * 32);   // grid-stride; capped at a multiple of the SM count
     switch (task) {
-    case 4: reward_kernel<E, 4, WANT_REWARD><<<grid, BLOCK, 0, st>>>(ag, dg, reward, success, m, reward_type); break;
-    case 5: reward_kernel<E, 5, WANT_REWARD><<<grid, BLOCK, 0, st>>>(ag, dg, reward, success, m, reward_type); break;
-    default: reward_kernel<E, 0, WANT_REWARD><<<grid, BLOCK, 0, st>>>(ag, dg, reward, success, m, reward_type); break;   // all 3-D position goals share thr 0.05
+    case 4: reward_kernel<E, 4, WANT_REWARD><<<grid, 256, 0, st>>>(ag, dg, reward, success, m, reward_type, vec_ok); break;
+    case 5: reward_kernel<E, 5, WANT_REWARD><<<grid, 256, 0, st>>>(ag, dg, reward, success, m, reward_type, vec_ok); break;
+    default: reward_kernel<E, 0, WANT_REWARD><<<grid, 256, 0, st>>>(ag, dg, reward, success, m, reward_type, vec_ok); break;   // all 3-D position goals share thr 0.05
     }
     g_launches++;
 }

@@ -347,37 +347,41 @@ __global__ void __launch_bounds__(BLOCK) ik_kernel(const __grid_constant__ EnvDe
 }
 
 // ---------------------------------------------------------------------------------------------- HER compute_reward / is_success
-// HBM-bound: M rows of two [M,G] arrays in, 4 (reward) or 1 (success) bytes out.  Rows are staged through shared memory with
-// 16-byte loads; 4 row-tiles per block keep enough loads in flight.
+// HBM-bound: M rows of two [M,G] arrays in, 4 (reward) or 1 (success) bytes out.  Each thread owns RPT consecutive rows chosen so
+// that RPT*G elements are a whole number of 16-byte words: the rows are fetched with streaming 16-byte loads straight into
+// registers (3 per array in flight per thread, no shared-memory round trip, no barrier), a warp covers one contiguous span.
+template <typename E, int G> struct RewardTile {
+    static constexpr int V = 16 / sizeof(E);                                   // elements per 16-byte word
+    static constexpr int RPT = (G % V == 0) ? 1 : ((2 * G) % V == 0 ? 2 : 4);  // rows per thread
+    static constexpr int NV = RPT * G / V;                                     // 16-byte words per thread and array
+};
 template <typename E, int TASK, bool WANT_REWARD>
-__global__ void __launch_bounds__(BLOCK) reward_kernel(const E* __restrict__ ag, const E* __restrict__ dg, float* __restrict__ reward, unsigned char* __restrict__ success, long long m, int reward_type) {
+__global__ void __launch_bounds__(256) reward_kernel(const E* __restrict__ ag, const E* __restrict__ dg, float* __restrict__ reward, unsigned char* __restrict__ success, long long m, int reward_type, int vec_ok) {
     constexpr int G = task_goal_dim(TASK);
-    __shared__ __align__(16) E s_a[BLOCK * G];
-    __shared__ __align__(16) E s_b[BLOCK * G];
-    for (long long row0 = (long long)blockIdx.x * BLOCK; row0 < m; row0 += (long long)gridDim.x * BLOCK) {
-        const long long base = row0 * G;
-        const int rows = (int)min((long long)BLOCK, m - row0), cnt = rows * G;
-        if ((((uintptr_t)(ag + base)) & 15) == 0 && (((uintptr_t)(dg + base)) & 15) == 0) {
-            constexpr int V = 16 / sizeof(E);
-            const int cv = cnt / V;
-            for (int i = threadIdx.x; i < cv; i += BLOCK) {
-                reinterpret_cast<float4*>(s_a)[i] = __ldcs(reinterpret_cast<const float4*>(ag + base) + i);
-                reinterpret_cast<float4*>(s_b)[i] = __ldcs(reinterpret_cast<const float4*>(dg + base) + i);
-            }
-            for (int i = cv * V + threadIdx.x; i < cnt; i += BLOCK) { s_a[i] = ag[base + i]; s_b[i] = dg[base + i]; }
-        } else {
-            for (int i = threadIdx.x; i < cnt; i += BLOCK) { s_a[i] = ag[base + i]; s_b[i] = dg[base + i]; }
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < rows) {
-            E a[G], b[G];
+    using TL = RewardTile<E, G>;
+    const E thr = sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK);
+    const long long groups = vec_ok ? m / TL::RPT : 0;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+        union { float4 v[TL::NV]; E e[TL::RPT * G]; } a, b;
+        const float4* pa = reinterpret_cast<const float4*>(ag + g * TL::RPT * G);
+        const float4* pb = reinterpret_cast<const float4*>(dg + g * TL::RPT * G);
 #pragma unroll
-            for (int k = 0; k < G; k++) { a[k] = s_a[threadIdx.x * G + k]; b[k] = s_b[threadIdx.x * G + k]; }
-            E d = goal_distance(TASK, a, b);
-            if (WANT_REWARD) reward[row0 + threadIdx.x] = reward_from_distance(reward_type, d, sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK));
-            else success[row0 + threadIdx.x] = d < (sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK));
+        for (int k = 0; k < TL::NV; k++) { a.v[k] = __ldcs(pa + k); b.v[k] = __ldcs(pb + k); }
+#pragma unroll
+        for (int r = 0; r < TL::RPT; r++) {
+            E d = goal_distance(TASK, a.e + r * G, b.e + r * G);
+            if (WANT_REWARD) reward[g * TL::RPT + r] = reward_from_distance(reward_type, d, thr);
+            else success[g * TL::RPT + r] = d < thr;
         }
-        __syncthreads();
+    }
+    // tail rows (and the whole array when the pointers are not 16-byte aligned)
+    for (long long row = groups * TL::RPT + (long long)blockIdx.x * blockDim.x + threadIdx.x; row < m; row += (long long)gridDim.x * blockDim.x) {
+        E a[G], b[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) { a[k] = ag[row * G + k]; b[k] = dg[row * G + k]; }
+        E d = goal_distance(TASK, a, b);
+        if (WANT_REWARD) reward[row] = reward_from_distance(reward_type, d, thr);
+        else success[row] = d < thr;
     }
 }
 
