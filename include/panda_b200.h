@@ -79,6 +79,9 @@ int pg_inverse_kinematics(pg_env* env, const double* position, const double* ori
 
 /* Episode statistics accumulated by auto-reset since creation: {episodes, successes, return_sum, length_sum} (host). */
 int pg_stats(pg_env* env, double out[4]);
+/* Scheduling introspection (host buffers): the per-env key byte written by the last step and the thread -> env map built from the
+ * previous one (bits 0-4 sub-steps with contacts, bit 6 full joint-limit sweep, bit 7 near a contact). */
+int pg_debug_schedule(pg_env* env, unsigned char* key, int* perm);
 /* Number of kernels this library has launched in this process. */
 long long pg_kernel_launches(void);
 const char* pg_last_error(void);

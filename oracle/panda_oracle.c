@@ -408,6 +408,8 @@ void po_restore_state(PoSim *s, const double *buf) {
 }
 int po_last_num_contacts(const PoSim *s) { return s->last_contacts; }
 int po_last_iterations(const PoSim *s) { return s->last_iters; }
+/* debug: number of arm joint-limit rows (joints 0..6) that ended the last sub-step with a non-zero impulse */
+int po_last_active_arm_limits(const PoSim *s) { int n = 0; for (int r = 0; r < 14; r++) n += s->rows[r].applied > 0; return n; }
 
 /* getLinkState: pose from the cached transforms FK(qc) (App. B.5); velocity = link-local velocity from the fresh
  * (q, qd) rotated to world by the cached basis.  pos = CoM-frame origin (pybullet.py:361 reads index [0]). */

@@ -56,6 +56,7 @@ void po_set_link_inertia(int link, double ixx, double iyy, double izz);
 void po_get_link_inertia(int link, double out[3]);
 int po_last_num_contacts(const PoSim *s);
 int po_last_iterations(const PoSim *s);
+int po_last_active_arm_limits(const PoSim *s);
 void po_mass_matrix(PoSim *s, double Minv[81]); /* inverse joint-space inertia at the current q */
 void po_get_link_def(int link, double out[16]);
 void po_get_robot_box(int i, double out[8]);

@@ -84,6 +84,7 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.goal = (T*)take(6 * n * sizeof(T));
     E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
     E.ccount = (unsigned char*)take(n); E.perm = (int*)take(n * sizeof(int));
+    E.hist = (int*)take(((n + PERM_CHUNK - 1) / PERM_CHUNK) * PERM_BUCKETS * sizeof(int));
     e->blob_bytes = off;
 }
 
@@ -171,7 +172,14 @@ int pg_step(pg_env* e, const float* actions, float* obs, float* ag, float* dg, f
     // contact-aware thread -> env map (see perm_kernel); small batches keep the identity map and the tiled I/O path
     int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
     const bool use_perm = e->sort_envs && e->n >= 4096;
-    if (use_perm) { perm_kernel<<<1, PERM_THREADS, 0, (cudaStream_t)stream>>>(e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, perm, e->n); g_launches++; }
+    if (use_perm) {
+        const unsigned char* key = e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount;
+        int* hist = e->precision == PG_F32 ? e->Ef.hist : e->Ed.hist;
+        const int nchunks = (e->n + PERM_CHUNK - 1) / PERM_CHUNK;
+        perm_hist_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, e->n);
+        perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, perm, e->n, nchunks);
+        g_launches += 2;
+    }
     EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
     if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
     if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, (cudaStream_t)stream);
@@ -307,6 +315,13 @@ int pg_inverse_kinematics(pg_env* e, const double* position, const double* orien
     else ik_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(e->Ed, position, orientation, joint_angles);
     g_launches++;
     PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_debug_schedule(pg_env* e, unsigned char* key_host, int* perm_host) {
+    if (!e || !key_host || !perm_host) return fail(PG_ERR_ARG, "pg_debug_schedule: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    PG_CUDA(cudaMemcpy(key_host, e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, (size_t)e->n, cudaMemcpyDeviceToHost));
+    PG_CUDA(cudaMemcpy(perm_host, e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm, (size_t)e->n * sizeof(int), cudaMemcpyDeviceToHost));
     return PG_OK;
 }
 int pg_stats(pg_env* e, double out[4]) {

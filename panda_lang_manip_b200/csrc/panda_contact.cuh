@@ -441,8 +441,11 @@ PG_HD void row_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T
 // One 2 ms stepSimulation: unconstrained velocities, contact generation at the current poses, <= 50 sequential-impulse sweeps
 // over [joint limits, motors] (direction alternating), contact normals, friction cones; exit when the largest squared
 // velocity change of a sweep is <= 1e-7; semi-implicit Euler.
-template <typename T, int NOBJ>
-PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C) {
+#ifdef PG_HOST_DEBUG
+static long g_dbg_fallbacks = 0, g_dbg_full_starts = 0;
+#endif
+template <typename T, int NOBJ, bool WATCH_LIMITS>
+PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep) {
     T sn[7], cs[7], Minv[ND][ND], qdd[ND];
     robot_dynamics(M, q, qd, sn, cs, Minv, qdd);
 #pragma unroll
@@ -489,9 +492,19 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
     const int nc = C.n;
+    // FAST: arm limit rows are only watched (exact no-ops while they rest at zero); if one would engage, redo with the full sweep
+    // WATCH_LIMITS is a measured policy: +19 % with joint control, -13 % with ee control (where contact rows dominate the sweep)
+    bool fast = WATCH_LIMITS && !full_sweep && !arm_limit_violated(M, q);
+    if (!fast) full_sweep = true;
+#ifdef PG_HOST_DEBUG
+    if (!fast) g_dbg_full_starts++;
+#endif
+    for (int attempt = 0; attempt < 2; attempt++) {
+    bool live = false;
     for (int it = 0; it < 50; it++) {
         T res = T(0);
-        joint_rows_sweep(M, Minv, R, dvq, it, res);
+        if (fast) joint_rows_sweep<true>(M, Minv, R, dvq, it, res, live); else joint_rows_sweep<false>(M, Minv, R, dvq, it, res, live);
+        if (live) break;
         if (nc > 0) {
             T d8[8], F8[8];
 #pragma unroll
@@ -595,6 +608,18 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
             }
         }
         if (res <= T(1e-7)) break;
+    }
+    if (!(fast && live)) break;
+    // an arm limit engaged: restart the solve from zero impulses with every row real
+    fast = false; full_sweep = true;
+#ifdef PG_HOST_DEBUG
+    g_dbg_fallbacks++;
+#endif
+#pragma unroll
+    for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+    for (int c = 0; c < nc; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
     }
 #pragma unroll
     for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }

@@ -502,26 +502,50 @@ template <int D, typename T> PG_HD void motor_row(const Model<T>& M, const T (*M
     for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * di;
     T r = di * Minv[D][D]; res = fmax(res, r * r);
 }
-template <int D, typename T> struct RowsFwd {
-    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, T>::lim(Mi, R, dv, res); limit_row<D, 0>(Mi, R, dv, res); limit_row<D, 1>(Mi, R, dv, res); }
-    static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, T>::mot(M, Mi, R, dv, res); motor_row<D>(M, Mi, R, dv, res); }
+// An arm limit row that rests at zero impulse and whose update would stay clamped at zero is an exact no-op, and that is the
+// state of the 14 arm limit rows in almost every sweep.  The FAST sweep therefore only *watches* them (same expression as the
+// real row, 3 instructions instead of 29) and raises `live` if one would have engaged; the caller then redoes the solve with
+// the full sweep.  Finger limit rows (the blocked gripper sits on its lower limit, an open one on the upper) stay real rows.
+template <int D, int SIDE, typename T> PG_HD void limit_watch(const JointRows<T>& R, const T* dv, bool& live) {
+    const T sg = SIDE == 0 ? T(1) : T(-1);
+    T sum = R.lim_app[2 * D + SIDE] + (R.lim_rhs[2 * D + SIDE] - sg * dv[D] * R.invD[D]);
+    live = live || (sum > T(0));
+}
+template <int D, bool FAST, typename T> struct RowsFwd {
+    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, bool& live) {
+        RowsFwd<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
+        if (FAST && D < 7) { limit_watch<D, 0>(R, dv, live); limit_watch<D, 1>(R, dv, live); }
+        else { limit_row<D, 0>(Mi, R, dv, res); limit_row<D, 1>(Mi, R, dv, res); }
+    }
+    static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, FAST, T>::mot(M, Mi, R, dv, res); motor_row<D>(M, Mi, R, dv, res); }
 };
-template <typename T> struct RowsFwd<-1, T> {
-    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&) {}
+template <bool FAST, typename T> struct RowsFwd<-1, FAST, T> {
+    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, bool&) {}
     static PG_HD void mot(const Model<T>&, const T (*)[ND], JointRows<T>&, T*, T&) {}
 };
-template <int D, typename T> struct RowsRev {
-    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { limit_row<D, 1>(Mi, R, dv, res); limit_row<D, 0>(Mi, R, dv, res); RowsRev<D - 1, T>::lim(Mi, R, dv, res); }
-    static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { motor_row<D>(M, Mi, R, dv, res); RowsRev<D - 1, T>::mot(M, Mi, R, dv, res); }
+template <int D, bool FAST, typename T> struct RowsRev {
+    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, bool& live) {
+        if (FAST && D < 7) { limit_watch<D, 1>(R, dv, live); limit_watch<D, 0>(R, dv, live); }
+        else { limit_row<D, 1>(Mi, R, dv, res); limit_row<D, 0>(Mi, R, dv, res); }
+        RowsRev<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
+    }
+    static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { motor_row<D>(M, Mi, R, dv, res); RowsRev<D - 1, FAST, T>::mot(M, Mi, R, dv, res); }
 };
-template <typename T> struct RowsRev<-1, T> {
-    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&) {}
+template <bool FAST, typename T> struct RowsRev<-1, FAST, T> {
+    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, bool&) {}
     static PG_HD void mot(const Model<T>&, const T (*)[ND], JointRows<T>&, T*, T&) {}
 };
 // one sweep over the non-contact rows; Bullet alternates the direction with the iteration parity
-template <typename T> PG_HD void joint_rows_sweep(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, int it, T& res) {
-    if (it & 1) { RowsFwd<ND - 1, T>::lim(Minv, R, dv, res); RowsFwd<ND - 1, T>::mot(M, Minv, R, dv, res); }
-    else { RowsRev<ND - 1, T>::mot(M, Minv, R, dv, res); RowsRev<ND - 1, T>::lim(Minv, R, dv, res); }
+template <bool FAST, typename T> PG_HD void joint_rows_sweep(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, int it, T& res, bool& live) {
+    if (it & 1) { RowsFwd<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); RowsFwd<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); }
+    else { RowsRev<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); RowsRev<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); }
+}
+// true when an arm joint sits on or beyond a limit at set-up: its row is live from the start, use the full sweep
+template <typename T> PG_HD bool arm_limit_violated(const Model<T>& M, const T* q) {
+    bool v = false;
+#pragma unroll
+    for (int d = 0; d < 7; d++) v = v || !(q[d] - M.lo[d] > T(0)) || !(M.hi[d] - q[d] > T(0));
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------- robot-only sub-step (Reach)
@@ -539,7 +563,8 @@ template <typename T> PG_HD void robot_substep(const Model<T>& M, T* q, T* qd, c
     for (int d = 0; d < ND; d++) dv[d] = T(0);
     for (int it = 0; it < 50; it++) {
         T res = T(0);
-        joint_rows_sweep(M, Minv, R, dv, it, res);
+        bool live = false;
+        joint_rows_sweep<false>(M, Minv, R, dv, it, res, live);
         if (res <= T(1e-7)) break;
     }
 #pragma unroll

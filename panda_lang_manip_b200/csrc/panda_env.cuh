@@ -152,15 +152,17 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
     constexpr int NOBJ = task_nobj(TASK);
     T target[ND], qc[ND];
     env_set_action<T, TASK, CTRL>(M, q, qd, action, target);
+    bool full_sweep = false;      // sticky within the step: once an arm limit engaged, later sub-steps start with the full sweep
     for (int s = 0; s < 20; s++) {
         if (s == 19) {
 #pragma unroll
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
-        env_substep<T, NOBJ>(M, S, q, qd, target, ob, C);
-        if (C.n > (max_contacts & 0x7f)) max_contacts = C.n | (max_contacts & 0x80);   // low 7 bits: largest contact count of the step
-        if (C.near) max_contacts |= 0x80;     // scheduling hint bit: close to a contact
+        env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep);
+        if (C.n > 0 && (max_contacts & 0x1f) < 20) max_contacts++;     // bits 0-4: number of sub-steps that had contacts
+        if (C.near) max_contacts |= 0x80;                              // bit 7: close to a contact
     }
+    if (full_sweep) max_contacts |= 0x40;                                             // bit 6: the full joint-limit sweep was needed
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
     float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);
     success = d < thr;

@@ -25,7 +25,8 @@ template <typename T> struct EnvDev {
     float* ret;                  // [n] running episode return
     double* stats;               // [4] episodes, successes, return sum, length sum
     int* perm;                   // [n] thread -> env map of the next step (contact-heavy envs first), or NULL
-    unsigned char* ccount;       // [n] largest contact count seen in the env's last step (the sort key)
+    unsigned char* ccount;       // [n] scheduling key written by the env's last step (contact count, full-sweep and near bits)
+    int* hist;                   // [ceil(n/1024)][24] scratch of the bucket sort
     Model<T> M;
     Scene<T> S;
 };
@@ -200,42 +201,37 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 // in index order nearly every warp holds a few envs in contact and runs that code at ~10% lane utilisation.  Before each step
 // the envs are therefore stably bucket-sorted by the contact count of their previous step (heaviest first so the long blocks
 // start early), which packs the contact work into full warps.  One block, two passes over per-thread chunks.
-constexpr int PERM_THREADS = 512, PERM_BUCKETS = 12;   // bucket: 0 far from any contact, 1 near one, 1 + min(contact count, 10); heaviest first
-__device__ __forceinline__ int perm_bucket(unsigned char key) { int c = key & 0x7f; return c > 0 ? 1 + min(c, PERM_BUCKETS - 2) : (key >> 7); }
-static __global__ void __launch_bounds__(PERM_THREADS) perm_kernel(const unsigned char* __restrict__ ccount, int* __restrict__ perm, int n) {
-    __shared__ int s_cnt[PERM_BUCKETS][PERM_THREADS];
-    __shared__ int s_base[PERM_BUCKETS];
-    const int t = threadIdx.x, chunk = (n + PERM_THREADS - 1) / PERM_THREADS, lo = min(n, t * chunk), hi = min(n, lo + chunk);
-    int cnt[PERM_BUCKETS];
-#pragma unroll
-    for (int b = 0; b < PERM_BUCKETS; b++) cnt[b] = 0;
-    for (int i = lo; i < hi; i++) {
-        int c = perm_bucket(ccount[i]);
-#pragma unroll
-        for (int b = 0; b < PERM_BUCKETS; b++) cnt[b] += (c == b);
-    }
-#pragma unroll
-    for (int b = 0; b < PERM_BUCKETS; b++) s_cnt[b][t] = cnt[b];
+// key byte: bits 0-4 number of sub-steps of the last step that had contacts (0..20), bit 6 the step needed the full joint-limit
+// sweep, bit 7 near a contact.  Envs in persistent contact, in transient contact, near and far end up in different warps.
+constexpr int PERM_BUCKETS = 44, PERM_CHUNK = 1024, PERM_THREADS = 256;
+__device__ __forceinline__ int perm_bucket(unsigned char key) {
+    int c = key & 0x1f, full = (key >> 6) & 1, near = key >> 7;
+    return full * 22 + (c > 0 ? 1 + min(c, 20) : near);
+}
+// pass 1: per-chunk bucket histogram
+static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const unsigned char* __restrict__ key, int* __restrict__ hist, int n) {
+    __shared__ int s_h[PERM_BUCKETS];
+    if (threadIdx.x < PERM_BUCKETS) s_h[threadIdx.x] = 0;
     __syncthreads();
-    for (int off = 1; off < PERM_THREADS; off <<= 1) {     // inclusive scan of every bucket's per-thread counts
-        int add[PERM_BUCKETS];
-#pragma unroll
-        for (int b = 0; b < PERM_BUCKETS; b++) add[b] = t >= off ? s_cnt[b][t - off] : 0;
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < PERM_BUCKETS; b++) s_cnt[b][t] += add[b];
-        __syncthreads();
-    }
-    if (t == 0) { int acc = 0; for (int b = PERM_BUCKETS - 1; b >= 0; b--) { s_base[b] = acc; acc += s_cnt[b][PERM_THREADS - 1]; } }
+    const int base = blockIdx.x * PERM_CHUNK;
+    for (int i = base + threadIdx.x; i < min(n, base + PERM_CHUNK); i += PERM_THREADS) atomicAdd(&s_h[perm_bucket(key[i])], 1);
     __syncthreads();
-    int pos[PERM_BUCKETS];
-#pragma unroll
-    for (int b = 0; b < PERM_BUCKETS; b++) pos[b] = s_base[b] + s_cnt[b][t] - cnt[b];
-    for (int i = lo; i < hi; i++) {
-        int c = perm_bucket(ccount[i]);
-#pragma unroll
-        for (int b = 0; b < PERM_BUCKETS; b++) if (c == b) perm[pos[b]++] = i;
+    if (threadIdx.x < PERM_BUCKETS) hist[blockIdx.x * PERM_BUCKETS + threadIdx.x] = s_h[threadIdx.x];
+}
+// pass 2: bucket-major offsets (heaviest bucket first; chunks in order inside a bucket) and scatter.  The order inside one chunk's
+// slice of a bucket is arbitrary: the map only decides which thread runs which env, never a result.
+static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned char* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks) {
+    __shared__ int s_tot[PERM_BUCKETS], s_pre[PERM_BUCKETS], s_pos[PERM_BUCKETS];
+    if (threadIdx.x < PERM_BUCKETS) {
+        int tot = 0, pre = 0;
+        for (int c = 0; c < nchunks; c++) { int h = hist[c * PERM_BUCKETS + threadIdx.x]; tot += h; if (c < (int)blockIdx.x) pre += h; }
+        s_tot[threadIdx.x] = tot; s_pre[threadIdx.x] = pre;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int b = PERM_BUCKETS - 1; b >= 0; b--) { s_pos[b] = acc + s_pre[b]; acc += s_tot[b]; } }
+    __syncthreads();
+    const int base = blockIdx.x * PERM_CHUNK;
+    for (int i = base + threadIdx.x; i < min(n, base + PERM_CHUNK); i += PERM_THREADS) perm[atomicAdd(&s_pos[perm_bucket(key[i])], 1)] = i;
 }
 template <int W, typename E> __device__ __forceinline__ void row_load(const E* g, int i, E* reg) {
 #pragma unroll

@@ -29,4 +29,11 @@ def hostcheck():
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
     import ctypes
-    return ctypes.CDLL(so)
+    lib = ctypes.CDLL(so)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.hc_env_step.argtypes = [ci, ci, ci, ci] + [vp] * 8
+    lib.hc_minv.argtypes = [ci] + [vp] * 5
+    lib.hc_substeps.argtypes = [ci, vp, vp, vp, vp, ci]
+    lib.hc_observe.argtypes = [ci] + [vp] * 6
+    lib.hc_ik.argtypes = [ci] + [vp] * 5
+    return lib

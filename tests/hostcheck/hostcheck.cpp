@@ -1,6 +1,7 @@
 // hostcheck.cpp -- TEST-ONLY host compilation of the device math in panda_lang_manip_b200/csrc/panda_dyn.cuh.
 // It lets the CPU test-suite (-m "not gpu") compare the kernel's formulation (RNEA + CRBA + Cholesky, unrolled) with the
 // oracle's (ABA + impulse responses) without a GPU.  It is NOT a fallback: nothing in the package loads this library.
+#define PG_HOST_DEBUG 1
 #include "../../panda_lang_manip_b200/csrc/panda_model.h"
 #include "../../panda_lang_manip_b200/csrc/panda_scene.h"
 #include <string.h>
@@ -62,6 +63,8 @@ template <typename T> static void env_step_d(int task, int ctrl, int reward, con
     }
 }
 extern "C" {
+long hc_dbg_fallbacks() { return pg::g_dbg_fallbacks; }
+long hc_dbg_full_starts() { return pg::g_dbg_full_starts; }
 void hc_env_step(int dbl, int task, int ctrl, int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
     if (dbl) env_step_d<double>(task, ctrl, reward, base, st, action, obs, ag, dg, rew, succ); else env_step_d<float>(task, ctrl, reward, base, st, action, obs, ag, dg, rew, succ);
 }
