@@ -47,6 +47,13 @@ int pg_reset(pg_env* env, const unsigned char* mask, const double* goal_override
  * obs/ag/dg rows hold the reset observation while reward/terminated/truncated describe the finished step. */
 int pg_step(pg_env* env, const float* actions, float* obs, float* achieved_goal, float* desired_goal, float* reward,
             unsigned char* terminated, unsigned char* truncated, int auto_reset, void* stream);
+/* The fork's orientation-target control (panda_gym/envs/robots/panda_ori.py:52-99: set_action(action, euler_xyz)): as pg_step, with a
+ * per-env EE target quaternion [N,4] (x,y,z,w; float32, normalised inside) fed to the IK instead of (1,0,0,0).  ee control only. */
+int pg_step_oriented(pg_env* env, const float* actions, const float* target_quat, float* obs, float* achieved_goal, float* desired_goal,
+                     float* reward, unsigned char* terminated, unsigned char* truncated, int auto_reset, void* stream);
+/* Action scaling of Panda.set_action: defaults 0.05 (ee / joint displacement, panda.py:81,103) and 0.2 (fingers, panda.py:65);
+ * the fork's panda_cartesian.py:67,157 uses 1.0 / 1.0. */
+int pg_set_action_scale(pg_env* env, double ee_scale, double finger_scale);
 /* Same call with HOST buffers: actions are copied to the device, the step runs, all outputs are copied back and the
  * stream is synchronised before returning (the end-to-end path a CPU learner uses). */
 int pg_step_host(pg_env* env, const float* actions, float* obs, float* achieved_goal, float* desired_goal, float* reward,

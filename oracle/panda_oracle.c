@@ -856,17 +856,22 @@ void po_env_reset(PoEnv *e, const double *goal, const double *objpos, float *obs
 void po_env_set_state(PoEnv *e, const double *q, const double *qd) { PoSim *s = e->sim; for (int d = 0; d < ND; d++) { s->q[d] = q[d]; s->qd[d] = qd[d]; s->qc[d] = q[d] - qd[d] * DT; } }
 void po_env_get_state(PoEnv *e, double *q, double *qd) { memcpy(q, e->sim->q, sizeof e->sim->q); memcpy(qd, e->sim->qd, sizeof e->sim->qd); }
 void po_env_step(PoEnv *e, const float *action, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated) {
+    po_env_step_oriented(e, action, NULL, 0.05, 0.2, obs, ag, dg, reward, terminated);
+}
+/* the fork's robots/panda_ori.py:52-99 (EE target orientation) and panda_cartesian.py:67,157 (unscaled actions) */
+void po_env_step_oriented(PoEnv *e, const float *action, const double *target_quat, double ee_scale, double finger_scale, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated) {
     PoSim *s = e->sim; double a[8], target[ND]; int na = po_env_action_dim(e);
     for (int k = 0; k < na; k++) { double v = action[k]; a[k] = v < -1 ? -1 : (v > 1 ? 1 : v); }
     if (e->control == PO_CTRL_EE) {
         double p[3], qt[4], lin[3], ang[3], tq[4] = {1, 0, 0, 0}, ik[ND];
+        if (target_quat) memcpy(tq, target_quat, sizeof tq);
         po_get_link_state(s, 11, p, qt, lin, ang);
-        for (int k = 0; k < 3; k++) p[k] += a[k] * 0.05;
+        for (int k = 0; k < 3; k++) p[k] += a[k] * ee_scale;
         if (p[2] < 0) p[2] = 0;
         po_inverse_kinematics(s, 11, p, tq, ik);
         for (int d = 0; d < 7; d++) target[d] = ik[d];
-    } else for (int d = 0; d < 7; d++) target[d] = s->q[d] + a[d] * 0.05;
-    double w = e->block_gripper ? 0.0 : (s->q[7] + s->q[8]) + a[na - 1] * 0.2;
+    } else for (int d = 0; d < 7; d++) target[d] = s->q[d] + a[d] * ee_scale;
+    double w = e->block_gripper ? 0.0 : (s->q[7] + s->q[8]) + a[na - 1] * finger_scale;
     target[7] = target[8] = w / 2;
     for (int d = 0; d < ND; d++) po_control_joint(s, DOF_LINK[d], target[d], FORCES[d]);
     po_step(s, 20);

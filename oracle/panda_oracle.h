@@ -73,6 +73,7 @@ int po_env_action_dim(const PoEnv *e);
 void po_env_reset(PoEnv *e, const double *goal, const double *objpos, float *obs, float *ag, float *dg);
 void po_env_set_state(PoEnv *e, const double *q, const double *qd);
 void po_env_get_state(PoEnv *e, double *q, double *qd);
+void po_env_step_oriented(PoEnv *e, const float *action, const double *target_quat, double ee_scale, double finger_scale, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated);
 void po_env_step(PoEnv *e, const float *action, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated);
 
 /* CPU baseline driver: random-action rollout of one env for n_steps env steps (reset on success / TimeLimit) */

@@ -17,7 +17,7 @@ REWARD = {"sparse": 0, "dense": 1}
 PRECISION = {"f32": 0, "f64": 1}
 
 SYMBOLS = [
-    "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_host", "pg_compute_reward", "pg_is_success",
+    "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_compute_reward", "pg_is_success",
     "pg_compute_reward_host", "pg_is_success_host", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_debug_schedule", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
@@ -49,6 +49,8 @@ def load() -> ctypes.CDLL:
     lib.pg_dims.argtypes = [vp, pi, pi, pi, pi, pi]
     lib.pg_reset.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp]
+    lib.pg_step_oriented.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp]
+    lib.pg_set_action_scale.argtypes = [vp, ctypes.c_double, ctypes.c_double]
     lib.pg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, c_int]
     lib.pg_compute_reward.argtypes = [c_int, c_int, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_is_success.argtypes = [c_int, vp, vp, vp, c_ll, c_int, vp]

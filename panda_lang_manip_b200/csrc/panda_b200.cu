@@ -166,9 +166,19 @@ int pg_reset(pg_env* e, const unsigned char* mask, const double* goal_override, 
 
 int pg_step(pg_env* e, const float* actions, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated, unsigned char* truncated,
             int auto_reset, void* stream) {
+    return pg_step_oriented(e, actions, nullptr, obs, ag, dg, reward, terminated, truncated, auto_reset, stream);
+}
+int pg_set_action_scale(pg_env* e, double ee_scale, double finger_scale) {
+    if (!e || !(ee_scale > 0) || !(finger_scale > 0)) return fail(PG_ERR_ARG, "pg_set_action_scale: bad argument");
+    e->Ef.M.ee_scale = (float)ee_scale; e->Ef.M.finger_scale = (float)finger_scale; e->Ed.M.ee_scale = ee_scale; e->Ed.M.finger_scale = finger_scale;
+    return PG_OK;
+}
+int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated,
+                     unsigned char* truncated, int auto_reset, void* stream) {
     if (!e || !actions) return fail(PG_ERR_ARG, "pg_step: NULL handle or actions");
+    if (target_quat && e->ctrl != CTRL_EE) return fail(PG_ERR_ARG, "pg_step_oriented: a target orientation needs ee control");
     PG_CUDA(cudaSetDevice(e->device));
-    StepIO io{actions, obs, ag, dg, reward, terminated, truncated, auto_reset};
+    StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset};
     // contact-aware thread -> env map (see perm_kernel); small batches keep the identity map and the tiled I/O path
     int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
     const bool use_perm = e->sort_envs && e->n >= 4096;

@@ -37,6 +37,7 @@ template <typename T> struct Model {
     T hz;                       // finger joint frame height above the link-6 origin (0.107 + 0.0584)
     T eez;                      // grasp-target frame height above the link-6 origin (0.107 + 0.105)
     T fa[2];                    // finger slide direction sign in hand axes (+1, -1)
+    T ee_scale, finger_scale;   // action scaling: 0.05 / 0.2 (panda.py:81,65); the fork's panda_cartesian.py:67,157 uses 1 / 1
 };
 
 template <typename T> struct Consts {

@@ -121,7 +121,7 @@ PG_HD void env_observe(const Model<T>& M, const T* q, const T* qd, const T* qc, 
 
 // Panda.set_action: clip, arm target from the ee displacement (IK) or the joint deltas, finger target
 template <typename T, int TASK, int CTRL>
-PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const float* action, T* target) {
+PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const float* action, const float* target_quat, T* target) {
     constexpr int NA = task_act_dim(TASK, CTRL);
     T a[NA];
 #pragma unroll
@@ -133,25 +133,34 @@ PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const floa
         for (int d = 0; d < ND; d++) qc[d] = q[d] - qd[d] * Consts<T>::dt;
         Frame<T> F[7]; fk_arm(M, qc, F);
         V3<T> p = F[6].p + F[6].Z * M.eez;
-        p.x += a[0] * T(0.05); p.y += a[1] * T(0.05); p.z += a[2] * T(0.05);
+        p.x += a[0] * M.ee_scale; p.y += a[1] * M.ee_scale; p.z += a[2] * M.ee_scale;
         if (p.z < T(0)) p.z = T(0);
-        const T tq[4] = {T(1), T(0), T(0), T(0)};
+        // target orientation: (1,0,0,0) as panda.py:89, or the caller's quaternion (the fork's panda_ori.py:72-99 euler_xyz target)
+        T tq[4] = {T(1), T(0), T(0), T(0)};
+        if (target_quat) {
+            T n = T(0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { tq[k] = (T)target_quat[k]; n += tq[k] * tq[k]; }
+            n = T(1) / sqrt(n);
+#pragma unroll
+            for (int k = 0; k < 4; k++) tq[k] *= n;
+        }
         ik_ee(M, q, p, tq, target);
     } else {
 #pragma unroll
-        for (int d = 0; d < 7; d++) target[d] = q[d] + a[d] * T(0.05);
+        for (int d = 0; d < 7; d++) target[d] = q[d] + a[d] * M.ee_scale;
     }
-    T w = task_block_gripper(TASK) ? T(0) : (q[7] + q[8]) + a[NA - 1] * T(0.2);
+    T w = task_block_gripper(TASK) ? T(0) : (q[7] + q[8]) + a[NA - 1] * M.finger_scale;
     target[7] = w / 2; target[8] = w / 2;
 }
 
 // RobotTaskEnv.step for one environment.  q/qd/ob are updated in place.
 template <typename T, int TASK, int CTRL>
-PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action,
+PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action, const float* target_quat,
                     float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& max_contacts) {
     constexpr int NOBJ = task_nobj(TASK);
     T target[ND], qc[ND];
-    env_set_action<T, TASK, CTRL>(M, q, qd, action, target);
+    env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
     bool full_sweep = false;      // sticky within the step: once an arm limit engaged, later sub-steps start with the full sweep
     for (int s = 0; s < 20; s++) {
         if (s == 19) {

@@ -31,6 +31,7 @@ template <typename T> struct EnvDev {
     Scene<T> S;
 };
 struct StepIO {
+    const float* target_quat;    // [n,4] (x,y,z,w) EE target orientation for ee control, or NULL = (1,0,0,0)
     const float* actions; float* obs; float* ag; float* dg; float* reward; unsigned char* terminated; unsigned char* truncated;
     int auto_reset;
 };
@@ -273,7 +274,9 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
         C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BLOCK;
         load_state<T, NOBJ>(E, i, q, qd, ob, goal);
         int max_contacts = 0;
-        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, obs, ag, dg, reward, term, C, max_contacts);
+        float tquat[4];
+        if (io.target_quat) row_load<4>(io.target_quat, i, tquat);
+        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, io.target_quat ? tquat : nullptr, obs, ag, dg, reward, term, C, max_contacts);
         int steps = E.steps[i] + 1;
         trunc = steps >= task_max_steps(TASK);
         float ret = E.ret[i] + reward;

@@ -77,6 +77,7 @@ template <typename T> Model<T> make_model(const double base[3]) {
     M.hz = (T)(kLinks[7].xyz[2] + kLinks[8].xyz[2]);
     M.eez = (T)(kLinks[7].xyz[2] + kEeZ);
     M.fa[0] = (T)1; M.fa[1] = (T)-1;
+    M.ee_scale = (T)0.05; M.finger_scale = (T)0.2;
     return M;
 }
 

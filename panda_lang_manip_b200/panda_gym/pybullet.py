@@ -28,6 +28,7 @@ class PyBullet:
         self._bodies_idx = {}
         self._vec = None
         self._pending_action = None
+        self._pending_orientation = None
         self._task_name = None
         self._last_obs = None
 
@@ -54,7 +55,9 @@ class PyBullet:
         if self._pending_action is None:
             raise _lib.PandaB200Error("PyBullet.step() needs a pending action: call robot.set_action(action) first (panda.py:52-70)")
         a = torch.as_tensor(np.asarray(self._pending_action, dtype=np.float32)[None, :])
-        obs, rew, term, trunc, _ = vec.step(a)
+        tq = None if self._pending_orientation is None else torch.as_tensor(np.asarray(self._pending_orientation, dtype=np.float32)[None, :])
+        obs, rew, term, trunc, _ = vec.step(a, target_orientation=tq)
+        self._pending_orientation = None
         self._last_obs = ({k: v[0].cpu().numpy() for k, v in obs.items()}, float(rew[0]), bool(term[0]))
         self._pending_action = None
 

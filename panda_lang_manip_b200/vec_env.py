@@ -79,11 +79,17 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_reset(self._h, _ptr(m), _ptr(g), _ptr(o), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), self._stream()))
         return self._obs_dict()
 
-    def step(self, actions: torch.Tensor) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, torch.Tensor, Dict]:
+    def set_action_scale(self, ee_scale: float = 0.05, finger_scale: float = 0.2) -> None:
+        """Action scaling of Panda.set_action (panda.py:65,81); the fork's panda_cartesian robot uses (1.0, 1.0)."""
+        _lib.check(self.lib.pg_set_action_scale(self._h, float(ee_scale), float(finger_scale)))
+
+    def step(self, actions: torch.Tensor, target_orientation: Optional[torch.Tensor] = None):
+        """One env step.  ``target_orientation`` [N,4] (x,y,z,w): EE orientation target of the fork's panda_ori robot (ee control)."""
         a = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if a.shape != (self.num_envs, self.action_dim):
             raise ValueError(f"actions must be [{self.num_envs}, {self.action_dim}], got {tuple(a.shape)}")
-        _lib.check(self.lib.pg_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), _ptr(self.reward),
+        tq = None if target_orientation is None else target_orientation.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, 4).contiguous()
+        _lib.check(self.lib.pg_step_oriented(self._h, _ptr(a), _ptr(tq), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), _ptr(self.reward),
                                     _ptr(self.terminated), _ptr(self.truncated), int(self.auto_reset), self._stream()))
         return self._obs_dict(), self.reward, self.terminated, self.truncated, {"is_success": self.terminated}
 

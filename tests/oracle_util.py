@@ -44,6 +44,7 @@ def load_oracle():
             getattr(lib, f).argtypes = [vp, ctypes.c_int, vp, vp]
         lib.po_env_reset.argtypes = [vp] * 6
         lib.po_env_step.argtypes = [vp] * 7
+        lib.po_env_step_oriented.argtypes = [vp, vp, vp, D, D, vp, vp, vp, vp, vp]
         lib.po_env_set_state.argtypes = [vp] * 3; lib.po_env_get_state.argtypes = [vp] * 3
         lib.po_save_state.argtypes = [vp, vp]; lib.po_restore_state.argtypes = [vp, vp]
         lib.po_last_num_contacts.argtypes = [vp]; lib.po_last_iterations.argtypes = [vp]
@@ -140,6 +141,13 @@ class OracleEnv:
         a = np.ascontiguousarray(action, np.float32)
         r, t = np.zeros(1, np.float32), np.zeros(1, np.uint8)
         self.lib.po_env_step(self.h, P(a), P(self.obs), P(self.ag), P(self.dg), P(r), P(t))
+        return self.obs.copy(), self.ag.copy(), self.dg.copy(), float(r[0]), bool(t[0])
+
+    def step_oriented(self, action, quat, ee_scale=0.05, finger_scale=0.2):
+        a = np.ascontiguousarray(action, np.float32)
+        tq = np.ascontiguousarray(quat, np.float64)
+        r, t = np.zeros(1, np.float32), np.zeros(1, np.uint8)
+        self.lib.po_env_step_oriented(self.h, P(a), P(tq), float(ee_scale), float(finger_scale), P(self.obs), P(self.ag), P(self.dg), P(r), P(t))
         return self.obs.copy(), self.ag.copy(), self.dg.copy(), float(r[0]), bool(t[0])
 
     def joints(self):

@@ -103,3 +103,19 @@ def test_her_compute_reward_numpy_batch():
     assert np.array_equal(env.task.is_success(ag, dg), np.linalg.norm(ag - dg, axis=-1) < 0.05)
     assert float(env.compute_reward(ag[0], dg[0], {})) == float(want[0])
     env.close()
+
+
+def test_panda_ori_robot_tilts_the_gripper():
+    """The fork's panda_ori.Panda.set_action(action, euler_xyz): commanding a tilted target orientation rotates the hand."""
+    import panda_lang_manip_b200.panda_gym as pg
+    from panda_lang_manip_b200.panda_gym.envs.robots.panda_ori import Panda as PandaOri
+    env = pg.make("PandaPickAndPlace-v3")
+    env.robot.__class__ = PandaOri
+    env.reset(seed=0)
+    q0 = np.array([env.sim.get_joint_angle("panda", j) for j in range(7)])
+    for _ in range(15):
+        env.robot.set_action(np.zeros(4, np.float32), euler_xyz=[180.0, 0.0, 60.0])
+        env.sim.step()
+    q1 = np.array([env.sim.get_joint_angle("panda", j) for j in range(7)])
+    assert abs(q1[6] - q0[6]) > 0.3           # the wrist joint turned towards the 60 degree yaw target
+    env.close()

@@ -218,3 +218,41 @@ def test_large_batch_properties():
     assert (st[:, :9] > lo - 1e-2).all() and (st[:, :9] < hi + 1e-2).all()
     assert (torch.linalg.norm(o[:, :3] - torch.tensor([-0.6, 0.0, 0.333], device="cuda"), dim=-1) < 1.2).all()
     env.close()
+
+
+def test_oriented_ee_control_parity():
+    """SURVEY section 8f rank 1 (the fork's robots/panda_ori.py:52-99 and panda_cartesian.py:67,157): a per-env EE target orientation
+    fed to the IK, with the fork's unscaled actions; per-step parity against the oracle at the Reach tolerances."""
+    import panda_lang_manip_b200 as p
+    from panda_lang_manip_b200.panda_gym.envs.robots.panda_ori import quat_from_euler_xyz_deg
+    from scipy.spatial.transform import Rotation as R
+    n, steps = 8, 30
+    rng = np.random.default_rng(9)
+    goals = rng.uniform([-0.15, -0.15, 0.05], [0.15, 0.15, 0.3], (n, 3))
+    env = p.PandaVecEnv("pick_and_place", n, control_type="ee", auto_reset=False)
+    env.set_action_scale(1.0, 1.0)
+    objs = np.stack([rng.uniform(-0.15, 0.15, n), rng.uniform(-0.15, 0.15, n), np.full(n, 0.02)], -1)
+    env.reset(goals=goals, object_positions=objs)
+    oracles = [OracleEnv("pick_and_place", "ee") for _ in range(n)]
+    for i, oe in enumerate(oracles):
+        oe.reset(goals[i], objs[i])
+    worst_q = worst_ee = 0.0
+    for t in range(steps):
+        eul = np.stack([180 + rng.uniform(-25, 25, n), rng.uniform(-25, 25, n), rng.uniform(-40, 40, n)], -1)
+        quats = np.array([quat_from_euler_xyz_deg(e) for e in eul])
+        assert np.allclose(np.abs((quats * R.from_euler("xyz", eul, degrees=True).as_quat()).sum(-1)), 1.0, atol=1e-12)
+        a = np.concatenate([rng.uniform(-0.03, 0.03, (n, 3)), rng.uniform(-0.02, 0.02, (n, 1))], -1).astype(np.float32)
+        obs, *_ = env.step(torch.from_numpy(a).cuda(), target_orientation=torch.from_numpy(quats.astype(np.float32)).cuda())
+        st = env.get_state().cpu().numpy()
+        og = obs["observation"].cpu().numpy()
+        for i, oe in enumerate(oracles):
+            ob, *_ = oe.step_oriented(a[i], quats[i].astype(np.float32).astype(np.float64), 1.0, 1.0)
+            q, qd = oe.joints()
+            worst_q = max(worst_q, np.abs(st[i, :9] - q).max()); worst_ee = max(worst_ee, np.abs(og[i, :3] - ob[:3]).max())
+            st[i, :9], st[i, 9:18] = q, qd
+            st[i, 18:31] = oe.object_state(0)
+        env.set_state(torch.from_numpy(st))
+    for oe in oracles:
+        oe.close()
+    env.close()
+    assert worst_q < 1e-4 and worst_ee < 1e-4, (worst_q, worst_ee)
