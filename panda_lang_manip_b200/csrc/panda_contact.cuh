@@ -441,70 +441,17 @@ PG_HD void row_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T
 // One 2 ms stepSimulation: unconstrained velocities, contact generation at the current poses, <= 50 sequential-impulse sweeps
 // over [joint limits, motors] (direction alternating), contact normals, friction cones; exit when the largest squared
 // velocity change of a sweep is <= 1e-7; semi-implicit Euler.
-#ifdef PG_HOST_DEBUG
-static long g_dbg_fallbacks = 0, g_dbg_full_starts = 0;
-#endif
-template <typename T, int NOBJ, bool WATCH_LIMITS>
-PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep) {
-    T sn[7], cs[7], Minv[ND][ND], qdd[ND];
-    robot_dynamics(M, q, qd, sn, cs, Minv, qdd);
-#pragma unroll
-    for (int d = 0; d < ND; d++) qd[d] += qdd[d] * Consts<T>::dt;
-    World<T, NOBJ> W;
-    {   // world frames from the sines / cosines already computed
-        Frame<T> B; B.X = mk<T>(1, 0, 0); B.Y = mk<T>(0, 1, 0); B.Z = mk<T>(0, 0, 1); B.p = ld3(M.base);
-        W.F[0] = fk_next<0>(M, B, sn[0], cs[0]); W.F[1] = fk_next<1>(M, W.F[0], sn[1], cs[1]); W.F[2] = fk_next<2>(M, W.F[1], sn[2], cs[2]);
-        W.F[3] = fk_next<3>(M, W.F[2], sn[3], cs[3]); W.F[4] = fk_next<4>(M, W.F[3], sn[4], cs[4]); W.F[5] = fk_next<5>(M, W.F[4], sn[5], cs[5]);
-        W.F[6] = fk_next<6>(M, W.F[5], sn[6], cs[6]);
-        const T k = Consts<T>::k45;
-        W.Rb.X = (W.F[6].X - W.F[6].Y) * k; W.Rb.Y = (W.F[6].X + W.F[6].Y) * k; W.Rb.Z = W.F[6].Z;
-        V3<T> ph = W.F[6].p + W.F[6].Z * (M.hz - T(0.0584));   // hand frame origin
-        V3<T> pf = W.F[6].p + W.F[6].Z * M.hz;
-        W.cb[0] = ph + rot_mul(W.Rb, ld3(S.rb_c[0]));
-        W.cb[1] = pf + W.Rb.Y * q[7] + rot_mul(W.Rb, ld3(S.rb_c[1]));
-        W.cb[2] = pf - W.Rb.Y * q[8] + rot_mul(W.Rb, ld3(S.rb_c[2]));
-    }
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) {
-        W.Ro[o] = quat_rot(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw);
-        obj_unconstrained(S, o, ob[o], W.Ro[o]);
-        const Rot<T>& R = W.Ro[o];
-        T ix = T(1) / S.Ic[o][0], iy = T(1) / S.Ic[o][1], iz = T(1) / S.Ic[o][2];
-        W.Iinv[o][0] = ix * R.X.x * R.X.x + iy * R.Y.x * R.Y.x + iz * R.Z.x * R.Z.x;
-        W.Iinv[o][1] = ix * R.X.x * R.X.y + iy * R.Y.x * R.Y.y + iz * R.Z.x * R.Z.y;
-        W.Iinv[o][2] = ix * R.X.x * R.X.z + iy * R.Y.x * R.Y.z + iz * R.Z.x * R.Z.z;
-        W.Iinv[o][3] = ix * R.X.y * R.X.y + iy * R.Y.y * R.Y.y + iz * R.Z.y * R.Z.y;
-        W.Iinv[o][4] = ix * R.X.y * R.X.z + iy * R.Y.y * R.Y.z + iz * R.Z.y * R.Z.z;
-        W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
-    }
-    JointRows<T> R;
-    joint_rows_setup(M, q, qd, target, Minv, R);
-    collect_contacts<T, NOBJ>(S, W, ob, C);
-    OpSpace<T> Op;
-    const bool robot_contacts = C.nr > 0;
-    if (robot_contacts) opspace_setup<T, NOBJ>(W, Minv, qd, C, Op);
-    rows_setup<T, NOBJ>(S, W, Op, ob, C);
-
-    T dvq[ND];
-    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
-#pragma unroll
-    for (int d = 0; d < ND; d++) dvq[d] = T(0);
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+// The sequential-impulse loop.  FAST: the 14 arm limit rows are only watched; returns true if one of them would have engaged
+// (the caller then restarts with FAST = false).  Two instantiations, so the hot loop carries only the rows it executes.
+template <typename T, int NOBJ, bool FAST>
+PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const T (*Minv)[ND], JointRows<T>& R,
+                     Contacts<T>& C, const Obj<T>* ob, const bool robot_contacts, T* dvq, V3<T>* dvl, V3<T>* dva) {
     const int nc = C.n;
-    // FAST: arm limit rows are only watched (exact no-ops while they rest at zero); if one would engage, redo with the full sweep
-    // WATCH_LIMITS is a measured policy: +19 % with joint control, -13 % with ee control (where contact rows dominate the sweep)
-    bool fast = WATCH_LIMITS && !full_sweep && !arm_limit_violated(M, q);
-    if (!fast) full_sweep = true;
-#ifdef PG_HOST_DEBUG
-    if (!fast) g_dbg_full_starts++;
-#endif
-    for (int attempt = 0; attempt < 2; attempt++) {
     bool live = false;
     for (int it = 0; it < 50; it++) {
         T res = T(0);
-        if (fast) joint_rows_sweep<true>(M, Minv, R, dvq, it, res, live); else joint_rows_sweep<false>(M, Minv, R, dvq, it, res, live);
-        if (live) break;
+        joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, live);
+        if (FAST && live) break;
         if (nc > 0) {
             T d8[8], F8[8];
 #pragma unroll
@@ -609,17 +556,85 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
         }
         if (res <= T(1e-7)) break;
     }
-    if (!(fast && live)) break;
-    // an arm limit engaged: restart the solve from zero impulses with every row real
-    fast = false; full_sweep = true;
+    return live;
+}
+
 #ifdef PG_HOST_DEBUG
-    g_dbg_fallbacks++;
+static long g_dbg_fallbacks = 0, g_dbg_full_starts = 0;
 #endif
+template <typename T, int NOBJ, bool WATCH_LIMITS>
+PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep, bool& limits_active) {
+    T sn[7], cs[7], Minv[ND][ND], qdd[ND];
+    robot_dynamics(M, q, qd, sn, cs, Minv, qdd);
 #pragma unroll
-    for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+    for (int d = 0; d < ND; d++) qd[d] += qdd[d] * Consts<T>::dt;
+    World<T, NOBJ> W;
+    {   // world frames from the sines / cosines already computed
+        Frame<T> B; B.X = mk<T>(1, 0, 0); B.Y = mk<T>(0, 1, 0); B.Z = mk<T>(0, 0, 1); B.p = ld3(M.base);
+        W.F[0] = fk_next<0>(M, B, sn[0], cs[0]); W.F[1] = fk_next<1>(M, W.F[0], sn[1], cs[1]); W.F[2] = fk_next<2>(M, W.F[1], sn[2], cs[2]);
+        W.F[3] = fk_next<3>(M, W.F[2], sn[3], cs[3]); W.F[4] = fk_next<4>(M, W.F[3], sn[4], cs[4]); W.F[5] = fk_next<5>(M, W.F[4], sn[5], cs[5]);
+        W.F[6] = fk_next<6>(M, W.F[5], sn[6], cs[6]);
+        const T k = Consts<T>::k45;
+        W.Rb.X = (W.F[6].X - W.F[6].Y) * k; W.Rb.Y = (W.F[6].X + W.F[6].Y) * k; W.Rb.Z = W.F[6].Z;
+        V3<T> ph = W.F[6].p + W.F[6].Z * (M.hz - T(0.0584));   // hand frame origin
+        V3<T> pf = W.F[6].p + W.F[6].Z * M.hz;
+        W.cb[0] = ph + rot_mul(W.Rb, ld3(S.rb_c[0]));
+        W.cb[1] = pf + W.Rb.Y * q[7] + rot_mul(W.Rb, ld3(S.rb_c[1]));
+        W.cb[2] = pf - W.Rb.Y * q[8] + rot_mul(W.Rb, ld3(S.rb_c[2]));
+    }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        W.Ro[o] = quat_rot(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw);
+        obj_unconstrained(S, o, ob[o], W.Ro[o]);
+        const Rot<T>& R = W.Ro[o];
+        T ix = T(1) / S.Ic[o][0], iy = T(1) / S.Ic[o][1], iz = T(1) / S.Ic[o][2];
+        W.Iinv[o][0] = ix * R.X.x * R.X.x + iy * R.Y.x * R.Y.x + iz * R.Z.x * R.Z.x;
+        W.Iinv[o][1] = ix * R.X.x * R.X.y + iy * R.Y.x * R.Y.y + iz * R.Z.x * R.Z.y;
+        W.Iinv[o][2] = ix * R.X.x * R.X.z + iy * R.Y.x * R.Y.z + iz * R.Z.x * R.Z.z;
+        W.Iinv[o][3] = ix * R.X.y * R.X.y + iy * R.Y.y * R.Y.y + iz * R.Z.y * R.Z.y;
+        W.Iinv[o][4] = ix * R.X.y * R.X.z + iy * R.Y.y * R.Y.z + iz * R.Z.y * R.Z.z;
+        W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
+    }
+    JointRows<T> R;
+    joint_rows_setup(M, q, qd, target, Minv, R);
+    collect_contacts<T, NOBJ>(S, W, ob, C);
+    OpSpace<T> Op;
+    const bool robot_contacts = C.nr > 0;
+    if (robot_contacts) opspace_setup<T, NOBJ>(W, Minv, qd, C, Op);
+    rows_setup<T, NOBJ>(S, W, Op, ob, C);
+
+    T dvq[ND];
+    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
+#pragma unroll
+    for (int d = 0; d < ND; d++) dvq[d] = T(0);
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
-    for (int c = 0; c < nc; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
+    // Arm limit rows are exact no-ops while they rest at zero impulse: the fast solve only watches them and, if one would engage,
+    // the solve restarts from zero impulses with every row real (bit-identical to always running the full sweep).
+    const int nc = C.n;
+    bool fast = WATCH_LIMITS && !full_sweep && !arm_limit_violated(M, q);
+#ifdef PG_HOST_DEBUG
+    if (!fast) g_dbg_full_starts++;
+#endif
+    bool live = false;
+    if (fast) live = pgs_solve<T, NOBJ, true>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+    if (!fast || live) {
+        full_sweep = true;
+        if (live) {
+#ifdef PG_HOST_DEBUG
+            g_dbg_fallbacks++;
+#endif
+#pragma unroll
+            for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+#pragma unroll
+            for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+            for (int c = 0; c < nc; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
+        }
+        pgs_solve<T, NOBJ, false>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+        bool any = false;       // did an arm limit row actually carry impulse?  (decides whether the next step starts with the full sweep)
+#pragma unroll
+        for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
+        limits_active = limits_active || any || live;
     }
 #pragma unroll
     for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }

@@ -161,17 +161,22 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
     constexpr int NOBJ = task_nobj(TASK);
     T target[ND], qc[ND];
     env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
-    bool full_sweep = false;      // sticky within the step: once an arm limit engaged, later sub-steps start with the full sweep
+    // sticky: once an arm limit engaged, later sub-steps (and, through the key's bit 6, the next step) start with the full sweep;
+    // it is dropped again after a step in which no arm limit row carried impulse
+    bool full_sweep = (max_contacts & 0x40) != 0, limits_active = false;
+    max_contacts = 0;
     for (int s = 0; s < 20; s++) {
         if (s == 19) {
 #pragma unroll
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
-        env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep);
+        // watched arm-limit rows: a measured policy -- +25 % with joint control, -13 % with ee control (contact rows dominate there and the
+        // fast instantiation schedules worse), so it is enabled for joint control only
+        env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
         if (C.n > 0 && (max_contacts & 0x1f) < 20) max_contacts++;     // bits 0-4: number of sub-steps that had contacts
         if (C.near) max_contacts |= 0x80;                              // bit 7: close to a contact
     }
-    if (full_sweep) max_contacts |= 0x40;                                             // bit 6: the full joint-limit sweep was needed
+    if (limits_active) max_contacts |= 0x40;                                          // bit 6: an arm joint limit was engaged
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
     float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);
     success = d < thr;

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
         Contacts<T> C;
         C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BLOCK;
         load_state<T, NOBJ>(E, i, q, qd, ob, goal);
-        int max_contacts = 0;
+        int max_contacts = E.ccount[i] & 0x40;      // in: bit 6 of the previous step's key; out: this step's key
         float tquat[4];
         if (io.target_quat) row_load<4>(io.target_quat, i, tquat);
         env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, io.target_quat ? tquat : nullptr, obs, ag, dg, reward, term, C, max_contacts);
