@@ -235,24 +235,24 @@ int pg_step_host(pg_env* e, const float* actions, float* obs, float* ag, float* 
 }
 
 int pg_compute_reward(int task, int reward_type, const void* ag, const void* dg, float* reward, long long m, int dtype, void* stream) {
+    if (m == 0) return PG_OK;       // an empty batch is valid (its pointers may be NULL)
     if (task < 0 || task > 5 || !ag || !dg || !reward || m < 0) return fail(PG_ERR_ARG, "pg_compute_reward: bad argument");
-    if (m == 0) return PG_OK;
     if (dtype == PG_F32) launch_reward<float, true>(task, (const float*)ag, (const float*)dg, reward, nullptr, m, reward_type, (cudaStream_t)stream);
     else launch_reward<double, true>(task, (const double*)ag, (const double*)dg, reward, nullptr, m, reward_type, (cudaStream_t)stream);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
 int pg_is_success(int task, const void* ag, const void* dg, unsigned char* success, long long m, int dtype, void* stream) {
-    if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success: bad argument");
     if (m == 0) return PG_OK;
+    if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success: bad argument");
     if (dtype == PG_F32) launch_reward<float, false>(task, (const float*)ag, (const float*)dg, nullptr, success, m, 0, (cudaStream_t)stream);
     else launch_reward<double, false>(task, (const double*)ag, (const double*)dg, nullptr, success, m, 0, (cudaStream_t)stream);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
 int pg_compute_reward_host(int task, int reward_type, const void* ag, const void* dg, float* reward, long long m, int dtype, int device) {
-    if (task < 0 || task > 5 || !ag || !dg || !reward || m < 0) return fail(PG_ERR_ARG, "pg_compute_reward_host: bad argument");
     if (m == 0) return PG_OK;
+    if (task < 0 || task > 5 || !ag || !dg || !reward || m < 0) return fail(PG_ERR_ARG, "pg_compute_reward_host: bad argument");
     PG_CUDA(cudaSetDevice(device));
     const size_t es = dtype == PG_F32 ? 4 : 8, bytes = (size_t)m * task_goal_dim(task) * es;
     void *da = nullptr, *db = nullptr; float* dr = nullptr;
@@ -265,8 +265,8 @@ int pg_compute_reward_host(int task, int reward_type, const void* ag, const void
 }
 
 int pg_is_success_host(int task, const void* ag, const void* dg, unsigned char* success, long long m, int dtype, int device) {
-    if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success_host: bad argument");
     if (m == 0) return PG_OK;
+    if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success_host: bad argument");
     PG_CUDA(cudaSetDevice(device));
     const size_t es = dtype == PG_F32 ? 4 : 8, bytes = (size_t)m * task_goal_dim(task) * es;
     void *da = nullptr, *db = nullptr; unsigned char* dr = nullptr;

@@ -256,3 +256,27 @@ def test_oriented_ee_control_parity():
         oe.close()
     env.close()
     assert worst_q < 1e-4 and worst_ee < 1e-4, (worst_q, worst_ee)
+
+
+def test_edge_cases_ragged_unaligned_empty():
+    """Ragged env counts (not a multiple of the 128-thread block, sorted and identity thread->env maps), unaligned goal views
+    (scalar path of the reward kernel), empty batches, host-buffer stepping, every task's kernels."""
+    import panda_lang_manip_b200 as p
+    for task, ctrl in (("reach", "joints"), ("reach", "ee"), ("pick_and_place", "ee"), ("stack", "joints"), ("slide", "ee"), ("flip", "ee")):
+        for n in (1, 130, 4096 + 37):
+            env = p.PandaVecEnv(task, n, control_type=ctrl, seed=1)
+            g = torch.Generator(device="cuda").manual_seed(0)
+            for t in range(2):
+                obs, rew, term, trunc, _ = env.step(torch.rand((n, env.action_dim), device="cuda", generator=g) * 2 - 1)
+            assert torch.isfinite(obs["observation"]).all() and obs["observation"].shape == (n, env.obs_dim)
+            ho, hr, ht, htr, _ = env.step_host(np.zeros((n, env.action_dim), np.float32))
+            assert np.isfinite(ho["observation"]).all() and hr.shape == (n,)
+            env.close()
+    ag = torch.rand((100003, 3), device="cuda"); dg = torch.rand((100003, 3), device="cuda")
+    full = p.compute_reward("reach", "dense", ag, dg)
+    view = p.compute_reward("reach", "dense", ag[1:], dg[1:])           # 12-byte offset: not 16-byte aligned
+    assert torch.equal(full[1:], view)
+    assert p.compute_reward("reach", "sparse", ag[:0], dg[:0]).shape == (0,)
+    assert p.is_success("stack", torch.rand((5, 6), device="cuda"), torch.rand((5, 6), device="cuda")).shape == (5,)
+    with pytest.raises(ValueError):
+        p.compute_reward("reach", "sparse", ag, dg[:, :2])
