@@ -84,6 +84,10 @@ int pg_set_state(pg_env* env, const double* state, const unsigned char* mask, vo
  * float64 -> joint angles [N,7] float64. */
 int pg_inverse_kinematics(pg_env* env, const double* position, const double* orientation, double* joint_angles, void* stream);
 
+/* End-effector (link 11) pose from the current joint state, rows [x y z qx qy qz qw] float64 (the fork's get_ee_position /
+ * get_ee_orientation, panda_gym/envs/robots/panda_cartesian.py:218-225). */
+int pg_get_ee_pose(pg_env* env, double* pose, void* stream);
+
 /* Episode statistics accumulated by auto-reset since creation: {episodes, successes, return_sum, length_sum} (host). */
 int pg_stats(pg_env* env, double out[4]);
 /* Scheduling introspection (host buffers): the per-env key byte written by the last step and the thread -> env map built from the

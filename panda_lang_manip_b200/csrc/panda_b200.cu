@@ -327,6 +327,16 @@ int pg_inverse_kinematics(pg_env* e, const double* position, const double* orien
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
+int pg_get_ee_pose(pg_env* e, double* pose, void* stream) {
+    if (!e || !pose) return fail(PG_ERR_ARG, "pg_get_ee_pose: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    const int grid = (e->n + BLOCK - 1) / BLOCK;
+    if (e->precision == PG_F32) ee_pose_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(e->Ef, pose);
+    else ee_pose_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(e->Ed, pose);
+    g_launches++;
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
 int pg_debug_schedule(pg_env* e, unsigned char* key_host, int* perm_host) {
     if (!e || !key_host || !perm_host) return fail(PG_ERR_ARG, "pg_debug_schedule: NULL argument");
     PG_CUDA(cudaSetDevice(e->device));

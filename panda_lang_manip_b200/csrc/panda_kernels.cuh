@@ -345,6 +345,22 @@ __global__ void __launch_bounds__(BLOCK) ik_kernel(const __grid_constant__ EnvDe
     for (int d = 0; d < 7; d++) out[(size_t)i * 7 + d] = (double)o[d];
 }
 
+// End-effector (link 11) pose from the CURRENT joint state (getLinkState with computeForwardKinematics, the fork's
+// get_ee_orientation): rows [x y z qx qy qz qw] in float64.
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) ee_pose_kernel(const __grid_constant__ EnvDev<T> E, double* out) {
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n) return;
+    T q[ND];
+    for (int d = 0; d < ND; d++) q[d] = E.q[d * E.n + i];
+    Frame<T> F[7]; fk_arm(E.M, q, F);
+    Frame<T> Ee; const T k = Consts<T>::k45;
+    Ee.p = F[6].p + F[6].Z * E.M.eez; Ee.X = (F[6].X - F[6].Y) * k; Ee.Y = (F[6].X + F[6].Y) * k; Ee.Z = F[6].Z;
+    T qt[4]; rot_to_quat(Ee, qt);
+    double* r = out + (size_t)i * 7;
+    r[0] = Ee.p.x; r[1] = Ee.p.y; r[2] = Ee.p.z; r[3] = qt[0]; r[4] = qt[1]; r[5] = qt[2]; r[6] = qt[3];
+}
+
 // ---------------------------------------------------------------------------------------------- HER compute_reward / is_success
 // HBM-bound: M rows of two [M,G] arrays in, 4 (reward) or 1 (success) bytes out.  Each thread owns RPT consecutive rows chosen so
 // that RPT*G elements are a whole number of 16-byte words: the rows are fetched with streaming 16-byte loads straight into

@@ -145,6 +145,12 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_inverse_kinematics(self._h, _ptr(p), _ptr(o), _ptr(out), self._stream()))
         return out
 
+    def ee_pose(self) -> torch.Tensor:
+        """[N,7] float64: end-effector position and quaternion (x,y,z,w) from the current joint state."""
+        out = torch.empty((self.num_envs, 7), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pg_get_ee_pose(self._h, _ptr(out), self._stream()))
+        return out
+
     def stats(self) -> np.ndarray:
         """{episodes, successes, return_sum, length_sum} accumulated by auto-reset on this device."""
         import ctypes

@@ -119,3 +119,25 @@ def test_panda_ori_robot_tilts_the_gripper():
     q1 = np.array([env.sim.get_joint_angle("panda", j) for j in range(7)])
     assert abs(q1[6] - q0[6]) > 0.3           # the wrist joint turned towards the 60 degree yaw target
     env.close()
+
+
+def test_panda_cartesian_motion_primitives_pick_up_the_cube():
+    """The fork's scripted layer (robots/panda_cartesian.py: move / grasp / release): open, move over the cube, descend, grasp, lift."""
+    import panda_lang_manip_b200.panda_gym as pg
+    from panda_lang_manip_b200.panda_gym.envs.robots.panda_cartesian import Panda as PandaCartesian
+    env = pg.make("PandaPickAndPlace-v3")
+    env.robot.__class__ = PandaCartesian
+    env.reset(seed=2)
+    robot, sim = env.robot, env.sim
+    cube = sim.get_base_position("object")
+    down = [180.0, 0.0, 0.0]
+    robot.release()
+    robot.move(cube + np.array([0.0, 0.0, 0.10]), down)
+    robot.move(cube + np.array([0.0, 0.0, 0.0]), down)
+    assert np.linalg.norm(robot.get_ee_position() - cube) < 0.01
+    robot.grasp()
+    robot.move(cube + np.array([0.0, 0.0, 0.15]), down)
+    lifted = sim.get_base_position("object")
+    assert lifted[2] > cube[2] + 0.10, (cube, lifted)
+    assert robot.get_fingers_width() > 0.03          # the fingers are held open by the 4 cm cube
+    env.close()
