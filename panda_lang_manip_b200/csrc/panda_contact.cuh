@@ -295,6 +295,10 @@ template <typename T, int NOBJ> PG_HD ContactCtx<T, NOBJ> contact_ctx(Contacts<T
     X.P = mk<T>(C.f(c, C_P), C.f(c, C_P + 1), C.f(c, C_P + 2));
     X.n = mk<T>(C.f(c, C_N), C.f(c, C_N + 1), C.f(c, C_N + 2));
     int code = (int)C.f(c, C_CODE);
+    if (NOBJ == 0) {    // robot-only scene: every contact is a robot box on the table
+        X.rb = (code & 7) - 1; X.s = T(1); X.soft = X.rb > 0; X.table = true;
+        return X;
+    }
     int A = (code & 7) - 1, B = ((code >> 3) & 7) - 1;
     X.soft = (code & 64) != 0; X.table = (code & 128) != 0;
     X.rb = (A >= 0 && A < 3) ? A : ((B >= 0 && B < 3) ? B : -1);
@@ -518,7 +522,20 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     if (len > lim) { T f = div_fast(lim, len); s1 *= f; s2 *= f; }
                     d1 = s1 - a1; d2 = s2 - a2;
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
-                    r1.apply(Op, d1, d8, F8); r2.apply(Op, d2, d8, F8);
+                    {   // both tangent impulses act at once (the cone solved them from the same state): one Lambda product for the
+                        // combined wrench  -d1 e_y + d2 e_x  at r
+                        V3<T> r = X.P - Op.O6;
+                        V3<T> fdir = mk<T>(d2, -d1, T(0));
+                        V3<T> m = cross(r, fdir);
+                        T fd = dot(Op.hy, fdir);
+                        T w[8] = {m.x, m.y, m.z, fdir.x, fdir.y, T(0), X.rb == 1 ? fd : T(0), X.rb == 2 ? -fd : T(0)};
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            d8[k] += Op.L[sidx(k, 0)] * w[0] + Op.L[sidx(k, 1)] * w[1] + Op.L[sidx(k, 2)] * w[2] + Op.L[sidx(k, 3)] * w[3] + Op.L[sidx(k, 4)] * w[4]
+                                   + Op.L[sidx(k, 6)] * w[6] + Op.L[sidx(k, 7)] * w[7];
+                            F8[k] += w[k];
+                        }
+                    }
                 } else {
                     V3<T> t1, t2; plane_space(X.n, t1, t2);
                     T w1[8], w2[8];

@@ -101,9 +101,9 @@ def test_reach_episode_parity_f64(control):
 
 @pytest.mark.parametrize("task", ["push", "slide", "pick_and_place", "stack", "flip"])
 def test_contact_tasks_short_horizon(task):
-    """Random actions, 25 steps free-running, fp32: typical env 2e-5 rad / 1e-4 m object pose, worst env 1e-3 rad / 2e-2 m (a tumbling object amplifies fp32 noise)."""
+    """Random actions, 25 steps free-running, fp32: typical env 2e-5 rad / 3e-4 m object pose, worst env 1e-3 rad / 2e-2 m (a tumbling object amplifies fp32 noise)."""
     e = _rollout(task, "ee", n_envs=8, steps=25, precision="f32", seed=3)
-    assert np.median(e["q_env"]) < 2e-5 and e["q"] < 1e-3 and np.median(e["obj_env"]) < 1e-4 and e["obj"] < 2e-2, e
+    assert np.median(e["q_env"]) < 2e-5 and e["q"] < 1e-3 and np.median(e["obj_env"]) < 3e-4 and e["obj"] < 2e-2, e
     assert e["rew"] == 0 and e["succ"] == 0, e
 
 
