@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 METRIC = "env-steps/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch from the committed `ncu --set full` capture
 # (profiles/r1_step_kernel_ncu_full_raw.csv); None where no capture exists for the configuration
-NCU_TRAFFIC = {("reach", "joints", 65536): 8318208}
+NCU_TRAFFIC = {("reach", "joints", 65536): 8390912}
 ENV_IDS = {"reach": "PandaReach", "push": "PandaPush", "slide": "PandaSlide", "pick_and_place": "PandaPickAndPlace", "stack": "PandaStack", "flip": "PandaFlip"}
 TASK_ID = {"reach": 0, "push": 1, "slide": 2, "pick_and_place": 3, "stack": 4, "flip": 5}
 # algorithmic bytes per env-step, fp32 SoA: read state+goal+action, write state+obs+ag+dg+reward+2 flags
