@@ -246,7 +246,7 @@ def run_gpu(args):
             "her_compute_reward": her,
             "clocks": clocks,
             "wall_s_timed_loop": t_wall,
-            "episode_stats": {"episodes": stats[0].item(), "success_rate": (stats[1] / stats[0]).item() if stats[0].item() > 0 else None,
+            "episode_stats": {"diverged_env_steps": env.diverged(), "episodes": stats[0].item(), "success_rate": (stats[1] / stats[0]).item() if stats[0].item() > 0 else None,
                               "mean_return": (stats[2] / stats[0]).item() if stats[0].item() > 0 else None},
         }
         if her:

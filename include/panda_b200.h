@@ -90,6 +90,8 @@ int pg_get_ee_pose(pg_env* env, double* pose, void* stream);
 
 /* Episode statistics accumulated by auto-reset since creation: {episodes, successes, return_sum, length_sum} (host). */
 int pg_stats(pg_env* env, double out[4]);
+/* Number of env-steps that ended in a non-finite state (counted; with auto_reset the env is truncated and restarted). */
+int pg_diverged(pg_env* env, long long* count);
 /* Scheduling introspection (host buffers): the per-env key byte written by the last step and the thread -> env map built from the
  * previous one (bits 0-4 sub-steps with contacts, bit 6 full joint-limit sweep, bit 7 near a contact). */
 int pg_debug_schedule(pg_env* env, unsigned char* key, int* perm);

@@ -78,7 +78,7 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.n = e->n; E.reward_type = e->reward; E.id0 = id0; E.seed = seed;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 255) & ~(size_t)255; return p; };
-    E.stats = (double*)take(4 * sizeof(double));
+    E.stats = (double*)take(8 * sizeof(double));
     E.q = (T*)take(9 * n * sizeof(T)); E.qd = (T*)take(9 * n * sizeof(T));
     E.obj = (T*)take((size_t)(e->nobj > 0 ? e->nobj : 1) * 13 * n * sizeof(T));
     E.goal = (T*)take(6 * n * sizeof(T));
@@ -342,6 +342,14 @@ int pg_debug_schedule(pg_env* e, unsigned char* key_host, int* perm_host) {
     PG_CUDA(cudaSetDevice(e->device));
     PG_CUDA(cudaMemcpy(key_host, e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, (size_t)e->n, cudaMemcpyDeviceToHost));
     PG_CUDA(cudaMemcpy(perm_host, e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm, (size_t)e->n * sizeof(int), cudaMemcpyDeviceToHost));
+    return PG_OK;
+}
+int pg_diverged(pg_env* e, long long* count) {
+    if (!e || !count) return fail(PG_ERR_ARG, "pg_diverged: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    double d = 0;
+    PG_CUDA(cudaMemcpy(&d, (e->precision == PG_F32 ? e->Ef.stats : e->Ed.stats) + 4, sizeof(double), cudaMemcpyDeviceToHost));
+    *count = (long long)d;
     return PG_OK;
 }
 int pg_stats(pg_env* e, double out[4]) {

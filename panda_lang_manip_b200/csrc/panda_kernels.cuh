@@ -23,7 +23,7 @@ template <typename T> struct EnvDev {
     int* steps;                  // [n] steps since reset (TimeLimit)
     unsigned* episode;           // [n] episodes started (RNG counter)
     float* ret;                  // [n] running episode return
-    double* stats;               // [4] episodes, successes, return sum, length sum
+    double* stats;               // [5] episodes, successes, return sum, length sum, diverged envs
     int* perm;                   // [n] thread -> env map of the next step (contact-heavy envs first), or NULL
     unsigned char* ccount;       // [n] scheduling key written by the env's last step (contact count, full-sweep and near bits)
     int* hist;                   // [ceil(n/1024)][24] scratch of the bucket sort
@@ -257,13 +257,13 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
     constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
     extern __shared__ __align__(16) unsigned char s_raw[];
     float* s_io = reinterpret_cast<float*>(s_raw);
-    __shared__ double s_stats[4];
+    __shared__ double s_stats[5];
     const long long row0 = (long long)blockIdx.x * BLOCK;
     const int t = (int)row0 + threadIdx.x;
     const bool valid = t < E.n;
     const bool mapped = E.perm != nullptr;               // block-uniform
     const int i = (valid && mapped) ? E.perm[t] : t;
-    if (threadIdx.x < 4) s_stats[threadIdx.x] = 0.0;
+    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0.0;
     float act[NA];
     if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA>(s_io, io.actions, row0, E.n, act);
     float obs[O], ag[G], dg[G], reward = 0.0f;
@@ -280,6 +280,13 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
         int steps = E.steps[i] + 1;
         trunc = steps >= task_max_steps(TASK);
         float ret = E.ret[i] + reward;
+        // divergence guard: a non-finite state is counted and, with auto-reset, the episode is cut (truncated) and the env restarted
+        T chk = T(0);
+#pragma unroll
+        for (int d = 0; d < ND; d++) chk += q[d] + qd[d];
+#pragma unroll
+        for (int o = 0; o < NOBJ; o++) chk += ob[o].pos.x + ob[o].pos.y + ob[o].pos.z + ob[o].qw + ob[o].lin.x + ob[o].lin.y + ob[o].lin.z + ob[o].ang.x + ob[o].ang.y + ob[o].ang.z;
+        if (!(fabs(chk) < T(1e30))) { atomicAdd(&s_stats[4], 1.0); if (io.auto_reset) { trunc = 1; term = 0; reward = 0.0f; ret = E.ret[i]; } }
         if (io.auto_reset && (term || trunc)) {
             atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)term); atomicAdd(&s_stats[2], (double)ret); atomicAdd(&s_stats[3], (double)steps);
             uint32_t ep = E.episode[i] + 1u;
@@ -306,7 +313,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
         if (io.truncated) io.truncated[i] = trunc;
     }
     __syncthreads();
-    if (threadIdx.x < 4 && s_stats[threadIdx.x] != 0.0) atomicAdd(&E.stats[threadIdx.x], s_stats[threadIdx.x]);
+    if (threadIdx.x < 5 && s_stats[threadIdx.x] != 0.0) atomicAdd(&E.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------- raw state exchange / IK

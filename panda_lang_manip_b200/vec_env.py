@@ -151,6 +151,14 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_get_ee_pose(self._h, _ptr(out), self._stream()))
         return out
 
+    def diverged(self) -> int:
+        """Env-steps that ended in a non-finite state since creation (0 in a healthy run)."""
+        import ctypes
+        torch.cuda.current_stream(self.device).synchronize()
+        c = ctypes.c_longlong()
+        _lib.check(self.lib.pg_diverged(self._h, ctypes.byref(c)))
+        return int(c.value)
+
     def stats(self) -> np.ndarray:
         """{episodes, successes, return_sum, length_sum} accumulated by auto-reset on this device."""
         import ctypes

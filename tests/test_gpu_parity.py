@@ -196,6 +196,11 @@ def test_auto_reset_truncation_and_stats():
     assert int((trunc | term).sum()) > 0 and bool(((trunc == 1) | (term == 1)).all()) or True
     st = env.stats()
     assert st[0] >= int(trunc.sum()) and st[3] > 0
+    assert env.diverged() == 0
+    bad = env.get_state(); bad[:7, 0] = float("nan")          # poison 7 envs: they are counted, truncated and restarted
+    env.set_state(bad)
+    _, _, term, trunc, _ = env.step(zero)
+    assert env.diverged() == 7 and int(trunc[:7].sum()) == 7 and bool(torch.isfinite(env.get_state()).all())
     env.close()
 
 
