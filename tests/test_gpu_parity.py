@@ -188,12 +188,13 @@ def test_auto_reset_truncation_and_stats():
     n = 512
     env = p.PandaVecEnv("reach", n, control_type="joints", seed=3)
     zero = torch.zeros((n, 7), device="cuda")
-    ntrunc = 0
+    term_seen = torch.zeros(n, dtype=torch.uint8, device="cuda")
     for t in range(50):
         _, _, term, trunc, _ = env.step(zero)
+        term_seen |= term
         if t < 49:
             assert int(trunc.sum()) == 0
-    assert int((trunc | term).sum()) > 0 and bool(((trunc == 1) | (term == 1)).all()) or True
+    assert bool(((trunc == 1) | (term_seen == 1)).all())      # at step 50 every env has either succeeded earlier (and restarted) or is truncated now
     st = env.stats()
     assert st[0] >= int(trunc.sum()) and st[3] > 0
     assert env.diverged() == 0
