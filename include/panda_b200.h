@@ -92,9 +92,10 @@ int pg_get_ee_pose(pg_env* env, double* pose, void* stream);
 int pg_stats(pg_env* env, double out[4]);
 /* Number of env-steps that ended in a non-finite state (counted; with auto_reset the env is truncated and restarted). */
 int pg_diverged(pg_env* env, long long* count);
-/* Scheduling introspection (host buffers): the per-env key byte written by the last step and the thread -> env map built from the
- * previous one (bits 0-4 sub-steps with contacts, bit 6 full joint-limit sweep, bit 7 near a contact). */
-int pg_debug_schedule(pg_env* env, unsigned char* key, int* perm);
+/* Scheduling introspection (host buffers): the per-env 16-bit key written by the last launch and the thread -> env map built from
+ * the previous one (bits 0-4 contacts at the end of the launch, bit 5 robot contact, bit 6 solver ran all sweeps, bit 7 near a
+ * contact, bit 9 full joint-limit sweep). */
+int pg_debug_schedule(pg_env* env, unsigned short* key, int* perm);
 /* Number of kernels this library has launched in this process. */
 long long pg_kernel_launches(void);
 const char* pg_last_error(void);

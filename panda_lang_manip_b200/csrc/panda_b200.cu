@@ -68,6 +68,7 @@ struct pg_env {
     EnvDev<float> Ef; EnvDev<double> Ed;
     std::map<int, void*> snaps; int next_snap = 0;
     bool sort_envs = true;                            // PG_SORT_ENVS=0 disables the contact-aware thread->env map (A/B measurements)
+    int segments = 4;                                 // launches per step for sorted batches: 20 with objects, 4 without; PG_SEGMENTS overrides (a divisor of 20)
     // host-buffer path: pinned staging + device I/O buffers + private stream
     cudaStream_t hstream = nullptr;
     float *h_act = nullptr, *h_out = nullptr; float* d_act = nullptr; float* d_out = nullptr; size_t out_floats = 0; size_t out_bytes = 0;
@@ -82,8 +83,9 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.q = (T*)take(9 * n * sizeof(T)); E.qd = (T*)take(9 * n * sizeof(T));
     E.obj = (T*)take((size_t)(e->nobj > 0 ? e->nobj : 1) * 13 * n * sizeof(T));
     E.goal = (T*)take(6 * n * sizeof(T));
+    E.target = (T*)take(9 * n * sizeof(T));
     E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
-    E.ccount = (unsigned char*)take(n); E.perm = (int*)take(n * sizeof(int));
+    E.ccount = (unsigned short*)take(n * sizeof(unsigned short)); E.perm = (int*)take(n * sizeof(int));
     E.hist = (int*)take(((n + PERM_CHUNK - 1) / PERM_CHUNK) * PERM_BUCKETS * sizeof(int));
     e->blob_bytes = off;
 }
@@ -127,6 +129,8 @@ int pg_create(int task, int control_type, int reward_type, int num_envs, int dev
     if (precision == PG_F32) { bind(e->Ef, e, (char*)e->blob, seed, env_id_offset); e->Ef.M = make_model<float>(base); e->Ef.S = make_scene<float>(task); }
     else { bind(e->Ed, e, (char*)e->blob, seed, env_id_offset); e->Ed.M = make_model<double>(base); e->Ed.S = make_scene<double>(task); }
     { const char* v = getenv("PG_SORT_ENVS"); if (v && v[0] == '0') e->sort_envs = false; }
+    e->segments = e->nobj > 0 ? 20 : 4;
+    { const char* v = getenv("PG_SEGMENTS"); if (v) { int k = atoi(v); if (k >= 1 && k <= 20 && 20 % k == 0) e->segments = k; } }
     *out = e;
     int rc = pg_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc != PG_OK) { pg_destroy(e); *out = nullptr; return rc; }
@@ -178,21 +182,26 @@ int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, 
     if (!e || !actions) return fail(PG_ERR_ARG, "pg_step: NULL handle or actions");
     if (target_quat && e->ctrl != CTRL_EE) return fail(PG_ERR_ARG, "pg_step_oriented: a target orientation needs ee control");
     PG_CUDA(cudaSetDevice(e->device));
-    StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset};
-    // contact-aware thread -> env map (see perm_kernel); small batches keep the identity map and the tiled I/O path
-    int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
+    // Contact-aware scheduling (see perm_*_kernel): large batches are re-sorted by their contact state before every launch, and a
+    // step is cut into `segments` launches of consecutive sub-steps so that envs which make contact mid-step are regrouped; small
+    // batches keep the identity map, one launch per step and the tiled I/O path.  Results do not depend on either choice.
     const bool use_perm = e->sort_envs && e->n >= 4096;
-    if (use_perm) {
-        const unsigned char* key = e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount;
-        int* hist = e->precision == PG_F32 ? e->Ef.hist : e->Ed.hist;
-        const int nchunks = (e->n + PERM_CHUNK - 1) / PERM_CHUNK;
-        perm_hist_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, e->n);
-        perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, perm, e->n, nchunks);
-        g_launches += 2;
-    }
+    const int segs = use_perm ? e->segments : 1;
+    const unsigned short* key = e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount;
+    int* hist = e->precision == PG_F32 ? e->Ef.hist : e->Ed.hist;
+    int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
     EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
     if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
-    if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, (cudaStream_t)stream);
+    for (int sg = 0; sg < segs; sg++) {
+        StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset, sg * 20 / segs, (sg + 1) * 20 / segs};
+        if (use_perm) {
+            const int nchunks = (e->n + PERM_CHUNK - 1) / PERM_CHUNK;
+            perm_hist_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, e->n);
+            perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, perm, e->n, nchunks);
+            g_launches += 2;
+        }
+        if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, (cudaStream_t)stream);
+    }
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
@@ -337,10 +346,10 @@ int pg_get_ee_pose(pg_env* e, double* pose, void* stream) {
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }
-int pg_debug_schedule(pg_env* e, unsigned char* key_host, int* perm_host) {
+int pg_debug_schedule(pg_env* e, unsigned short* key_host, int* perm_host) {
     if (!e || !key_host || !perm_host) return fail(PG_ERR_ARG, "pg_debug_schedule: NULL argument");
     PG_CUDA(cudaSetDevice(e->device));
-    PG_CUDA(cudaMemcpy(key_host, e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, (size_t)e->n, cudaMemcpyDeviceToHost));
+    PG_CUDA(cudaMemcpy(key_host, e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, (size_t)e->n * sizeof(unsigned short), cudaMemcpyDeviceToHost));
     PG_CUDA(cudaMemcpy(perm_host, e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm, (size_t)e->n * sizeof(int), cudaMemcpyDeviceToHost));
     return PG_OK;
 }

@@ -137,6 +137,7 @@ template <typename T> struct Contacts {
     CStore<T> st;
     int n, nr, cap;
     bool near;                  // the gripper is within 3 cm of the table or inside an object's broad-phase sphere (scheduling hint)
+    bool capped;                // the last solve ran (nearly) all 50 sweeps (scheduling hint)
     PG_HD T& f(int c, int k) { return st.at(JX_SLOTS + c * REC + k); }
     PG_HD T& jx(int j, int a) { return st.at(6 * j + a); }
 };
@@ -441,6 +442,10 @@ PG_HD void row_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T
     }
 }
 
+#ifdef PG_HOST_DEBUG
+static long g_dbg_fallbacks = 0, g_dbg_full_starts = 0, g_dbg_sweeps = 0, g_dbg_solves = 0, g_dbg_contacts = 0;
+static int g_dbg_trace[4096], g_dbg_ntrace = 0;
+#endif
 // ---------------------------------------------------------------------------------------------- full sub-step
 // One 2 ms stepSimulation: unconstrained velocities, contact generation at the current poses, <= 50 sequential-impulse sweeps
 // over [joint limits, motors] (direction alternating), contact normals, friction cones; exit when the largest squared
@@ -452,7 +457,8 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                      Contacts<T>& C, const Obj<T>* ob, const bool robot_contacts, T* dvq, V3<T>* dvl, V3<T>* dva) {
     const int nc = C.n;
     bool live = false;
-    for (int it = 0; it < 50; it++) {
+    int it = 0;
+    for (; it < 50; it++) {
         T res = T(0);
         joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, live);
         if (FAST && live) break;
@@ -571,14 +577,19 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                 }
             }
         }
+#ifdef PG_HOST_DEBUG
+        g_dbg_sweeps++;
+#endif
         if (res <= T(1e-7)) break;
     }
+#ifdef PG_HOST_DEBUG
+    g_dbg_solves++; g_dbg_contacts += nc;
+    if (g_dbg_ntrace < 4096) g_dbg_trace[g_dbg_ntrace++] = it | (nc << 8) | (C.nr << 16);
+#endif
+    C.capped = it >= 49;
     return live;
 }
 
-#ifdef PG_HOST_DEBUG
-static long g_dbg_fallbacks = 0, g_dbg_full_starts = 0;
-#endif
 template <typename T, int NOBJ, bool WATCH_LIMITS>
 PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep, bool& limits_active) {
     T sn[7], cs[7], Minv[ND][ND], qdd[ND];

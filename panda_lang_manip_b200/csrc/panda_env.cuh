@@ -154,18 +154,25 @@ PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const floa
     target[7] = w / 2; target[8] = w / 2;
 }
 
-// RobotTaskEnv.step for one environment.  q/qd/ob are updated in place.
+// Scheduling key (16 bits) written by every launch for the sort that precedes the next one: bits 0-4 contacts of the last sub-step,
+// then: a robot box is in contact, the last solve ran all 50 sweeps, near a contact (or in contact earlier in the launch), an arm
+// joint limit was engaged (the next launch starts with the full limit sweep).
+enum { KEY_ROBOT = 0x20, KEY_CAPPED = 0x40, KEY_NEAR = 0x80, KEY_FULL = 0x200 };
+
+// RobotTaskEnv.step for one environment, or the sub-step range [s0, s1) of it (a step may be cut into segments so that the envs can
+// be re-sorted in between; the motor targets travel through `target`).  q/qd/ob are updated in place; the observation, goals,
+// reward and success are produced by the segment that ends the step (s1 == 20).
 template <typename T, int TASK, int CTRL>
 PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action, const float* target_quat,
-                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& max_contacts) {
+                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& sched_key, T* target, int s0 = 0, int s1 = 20) {
     constexpr int NOBJ = task_nobj(TASK);
-    T target[ND], qc[ND];
-    env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
-    // sticky: once an arm limit engaged, later sub-steps (and, through the key's bit 6, the next step) start with the full sweep;
-    // it is dropped again after a step in which no arm limit row carried impulse
-    bool full_sweep = (max_contacts & 0x40) != 0, limits_active = false;
-    max_contacts = 0;
-    for (int s = 0; s < 20; s++) {
+    T qc[ND];
+    if (s0 == 0) env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
+    // sticky: once an arm limit engaged, later sub-steps (and, through the key's KEY_FULL bit, the next segment / step) start with the
+    // full sweep; it is dropped again after a segment in which no arm limit row carried impulse
+    bool full_sweep = (sched_key & KEY_FULL) != 0, limits_active = false;
+    int nsub_contact = 0; bool near = false;
+    for (int s = s0; s < s1; s++) {
         if (s == 19) {
 #pragma unroll
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
@@ -173,10 +180,12 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
         // watched arm-limit rows: a measured policy -- +25 % with joint control, -13 % with ee control (contact rows dominate there and the
         // fast instantiation schedules worse), so it is enabled for joint control only
         env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
-        if (C.n > 0 && (max_contacts & 0x1f) < 20) max_contacts++;     // bits 0-4: number of sub-steps that had contacts
-        if (C.near) max_contacts |= 0x80;                              // bit 7: close to a contact
+        if (C.n > 0) nsub_contact++;
+        near = near || C.near;
     }
-    if (limits_active) max_contacts |= 0x40;                                          // bit 6: an arm joint limit was engaged
+    // scheduling key for the next launch (see perm_bucket): the contact picture of this launch's last sub-step
+    sched_key = (C.n < 31 ? C.n : 31) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (limits_active ? KEY_FULL : 0);
+    if (s1 < 20) return;
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
     float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);
     success = d < thr;

@@ -20,12 +20,13 @@ template <typename T> struct EnvDev {
     T* qd;                       // [9][n]
     T* obj;                      // [nobj][13][n]  pos3 quat4 lin3 ang3
     T* goal;                     // [6][n]
+    T* target;                   // [9][n] motor targets of the step in flight (only live between the segments of a cut step)
     int* steps;                  // [n] steps since reset (TimeLimit)
     unsigned* episode;           // [n] episodes started (RNG counter)
     float* ret;                  // [n] running episode return
     double* stats;               // [5] episodes, successes, return sum, length sum, diverged envs
     int* perm;                   // [n] thread -> env map of the next step (contact-heavy envs first), or NULL
-    unsigned char* ccount;       // [n] scheduling key written by the env's last step (contact count, full-sweep and near bits)
+    unsigned short* ccount;      // [n] scheduling key written by the env's last launch (see KEY_* in panda_env.cuh)
     int* hist;                   // [ceil(n/1024)][24] scratch of the bucket sort
     Model<T> M;
     Scene<T> S;
@@ -34,6 +35,7 @@ struct StepIO {
     const float* target_quat;    // [n,4] (x,y,z,w) EE target orientation for ee control, or NULL = (1,0,0,0)
     const float* actions; float* obs; float* ag; float* dg; float* reward; unsigned char* terminated; unsigned char* truncated;
     int auto_reset;
+    int s0, s1;                  // sub-step range of this launch: [0,20) = a whole step
 };
 struct ResetIO {
     const unsigned char* mask; const double* goal_override; const double* object_override; float* obs; float* ag; float* dg;
@@ -199,18 +201,19 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 
 // ---------------------------------------------------------------------------------------------- step
 // Contact-aware scheduling.  Contact handling is the expensive, data-dependent part of a sub-step; with envs mapped to threads
-// in index order nearly every warp holds a few envs in contact and runs that code at ~10% lane utilisation.  Before each step
-// the envs are therefore stably bucket-sorted by the contact count of their previous step (heaviest first so the long blocks
-// start early), which packs the contact work into full warps.  One block, two passes over per-thread chunks.
-// key byte: bits 0-4 number of sub-steps of the last step that had contacts (0..20), bit 6 the step needed the full joint-limit
-// sweep, bit 7 near a contact.  Envs in persistent contact, in transient contact, near and far end up in different warps.
-constexpr int PERM_BUCKETS = 44, PERM_CHUNK = 1024, PERM_THREADS = 256;
-__device__ __forceinline__ int perm_bucket(unsigned char key) {
-    int c = key & 0x1f, full = (key >> 6) & 1, near = key >> 7;
-    return full * 22 + (c > 0 ? 1 + min(c, 20) : near);
+// in index order nearly every warp holds a few envs in contact and runs that code at ~10% lane utilisation.  Before each launch
+// the envs are therefore bucket-sorted by the key their previous launch wrote (KEY_* in panda_env.cuh): full-limit-sweep envs,
+// envs with robot contacts, near ones, by contact count and solver cap -- heaviest first so the long blocks start early.
+// This packs envs that will execute the same contact code into the same warps.  Two passes over 1024-env chunks.
+constexpr int PERM_BUCKETS = 168, PERM_CHUNK = 1024, PERM_THREADS = 256;
+__device__ __forceinline__ int perm_bucket(unsigned short key) {
+    const int n = key & 0x1f, robot = (key >> 5) & 1, capped = (key >> 6) & 1, near = (key >> 7) & 1, full = (key >> 9) & 1;
+    const int nq = n <= 10 ? n : 11 + min((n - 11) >> 2, 2);        // 0..13
+    const int cls = robot ? 2 : near;
+    return ((full * 3 + cls) * 14 + nq) * 2 + capped;
 }
 // pass 1: per-chunk bucket histogram
-static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const unsigned char* __restrict__ key, int* __restrict__ hist, int n) {
+static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const unsigned short* __restrict__ key, int* __restrict__ hist, int n) {
     __shared__ int s_h[PERM_BUCKETS];
     if (threadIdx.x < PERM_BUCKETS) s_h[threadIdx.x] = 0;
     __syncthreads();
@@ -221,15 +224,20 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const un
 }
 // pass 2: bucket-major offsets (heaviest bucket first; chunks in order inside a bucket) and scatter.  The order inside one chunk's
 // slice of a bucket is arbitrary: the map only decides which thread runs which env, never a result.
-static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned char* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks) {
-    __shared__ int s_tot[PERM_BUCKETS], s_pre[PERM_BUCKETS], s_pos[PERM_BUCKETS];
-    if (threadIdx.x < PERM_BUCKETS) {
-        int tot = 0, pre = 0;
-        for (int c = 0; c < nchunks; c++) { int h = hist[c * PERM_BUCKETS + threadIdx.x]; tot += h; if (c < (int)blockIdx.x) pre += h; }
-        s_tot[threadIdx.x] = tot; s_pre[threadIdx.x] = pre;
-    }
+static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned short* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks) {
+    __shared__ int s_pos[PERM_BUCKETS], s_warp[PERM_THREADS / 32];
+    // thread t owns bucket PERM_BUCKETS-1-t (descending order): total over all chunks, prefix over the chunks before this one
+    const int b = PERM_BUCKETS - 1 - (int)threadIdx.x;
+    int tot = 0, pre = 0;
+    if (b >= 0) for (int c = 0; c < nchunks; c++) { int h = hist[c * PERM_BUCKETS + b]; tot += h; if (c < (int)blockIdx.x) pre += h; }
+    int x = tot;                                    // inclusive scan of the totals in descending bucket order
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
     __syncthreads();
-    if (threadIdx.x == 0) { int acc = 0; for (int b = PERM_BUCKETS - 1; b >= 0; b--) { s_pos[b] = acc + s_pre[b]; acc += s_tot[b]; } }
+    int carry = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) carry += s_warp[w];
+    if (b >= 0) s_pos[b] = carry + x - tot + pre;
     __syncthreads();
     const int base = blockIdx.x * PERM_CHUNK;
     for (int i = base + threadIdx.x; i < min(n, base + PERM_CHUNK); i += PERM_THREADS) perm[atomicAdd(&s_pos[perm_bucket(key[i])], 1)] = i;
@@ -264,41 +272,54 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
     const bool mapped = E.perm != nullptr;               // block-uniform
     const int i = (valid && mapped) ? E.perm[t] : t;
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0.0;
+    const bool first = io.s0 == 0, last = io.s1 == 20;      // launch-uniform
     float act[NA];
-    if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA>(s_io, io.actions, row0, E.n, act);
+    if (first) { if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA>(s_io, io.actions, row0, E.n, act); }
     float obs[O], ag[G], dg[G], reward = 0.0f;
     unsigned char term = 0, trunc = 0;
     if (valid) {
-        T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+        T q[ND], qd[ND], goal[6], target[ND]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         Contacts<T> C;
         C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BLOCK;
         load_state<T, NOBJ>(E, i, q, qd, ob, goal);
-        int max_contacts = E.ccount[i] & 0x40;      // in: bit 6 of the previous step's key; out: this step's key
+        if (!first) {
+#pragma unroll
+            for (int d = 0; d < ND; d++) target[d] = E.target[d * E.n + i];
+        }
+        int sched_key = E.ccount[i];                // in: KEY_FULL of the previous key; out: this launch's key
         float tquat[4];
-        if (io.target_quat) row_load<4>(io.target_quat, i, tquat);
-        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, io.target_quat ? tquat : nullptr, obs, ag, dg, reward, term, C, max_contacts);
-        int steps = E.steps[i] + 1;
-        trunc = steps >= task_max_steps(TASK);
-        float ret = E.ret[i] + reward;
-        // divergence guard: a non-finite state is counted and, with auto-reset, the episode is cut (truncated) and the env restarted
-        T chk = T(0);
+        if (first && io.target_quat) row_load<4>(io.target_quat, i, tquat);
+        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, (first && io.target_quat) ? tquat : nullptr, obs, ag, dg, reward, term, C, sched_key,
+                                target, io.s0, io.s1);
+        if (last) {
+            int steps = E.steps[i] + 1;
+            trunc = steps >= task_max_steps(TASK);
+            float ret = E.ret[i] + reward;
+            // divergence guard: a non-finite state is counted and, with auto-reset, the episode is cut (truncated) and the env restarted
+            T chk = T(0);
 #pragma unroll
-        for (int d = 0; d < ND; d++) chk += q[d] + qd[d];
+            for (int d = 0; d < ND; d++) chk += q[d] + qd[d];
 #pragma unroll
-        for (int o = 0; o < NOBJ; o++) chk += ob[o].pos.x + ob[o].pos.y + ob[o].pos.z + ob[o].qw + ob[o].lin.x + ob[o].lin.y + ob[o].lin.z + ob[o].ang.x + ob[o].ang.y + ob[o].ang.z;
-        if (!(fabs(chk) < T(1e30))) { atomicAdd(&s_stats[4], 1.0); if (io.auto_reset) { trunc = 1; term = 0; reward = 0.0f; ret = E.ret[i]; } }
-        if (io.auto_reset && (term || trunc)) {
-            atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)term); atomicAdd(&s_stats[2], (double)ret); atomicAdd(&s_stats[3], (double)steps);
-            uint32_t ep = E.episode[i] + 1u;
-            env_reset<T, TASK>(E, i, ep, nullptr, nullptr, q, qd, ob, goal);
+            for (int o = 0; o < NOBJ; o++) chk += ob[o].pos.x + ob[o].pos.y + ob[o].pos.z + ob[o].qw + ob[o].lin.x + ob[o].lin.y + ob[o].lin.z + ob[o].ang.x + ob[o].ang.y + ob[o].ang.z;
+            if (!(fabs(chk) < T(1e30))) { atomicAdd(&s_stats[4], 1.0); if (io.auto_reset) { trunc = 1; term = 0; reward = 0.0f; ret = E.ret[i]; } }
+            if (io.auto_reset && (term || trunc)) {
+                atomicAdd(&s_stats[0], 1.0); atomicAdd(&s_stats[1], (double)term); atomicAdd(&s_stats[2], (double)ret); atomicAdd(&s_stats[3], (double)steps);
+                uint32_t ep = E.episode[i] + 1u;
+                env_reset<T, TASK>(E, i, ep, nullptr, nullptr, q, qd, ob, goal);
 #pragma unroll
-            for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
-            E.episode[i] = ep; steps = 0; ret = 0.0f; max_contacts = 0;
-            env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
+                for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
+                E.episode[i] = ep; steps = 0; ret = 0.0f; sched_key = 0;
+                env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
+            }
+            E.steps[i] = steps; E.ret[i] = ret;
+        } else {
+#pragma unroll
+            for (int d = 0; d < ND; d++) E.target[d * E.n + i] = target[d];
         }
         store_state<T, NOBJ>(E, i, q, qd, ob);
-        E.steps[i] = steps; E.ret[i] = ret; E.ccount[i] = (unsigned char)max_contacts;
+        E.ccount[i] = (unsigned short)sched_key;
     }
+    if (!last) return;
     __syncthreads();    // the solver slab is dead for every thread of the block: reuse it as the output tile
     if (mapped) {
         if (valid) { row_store<O>(io.obs, i, obs); row_store<G>(io.ag, i, ag); row_store<G>(io.dg, i, dg); }

@@ -45,7 +45,7 @@ template <typename T, int TASK, int CTRL> static void env_step_t(int reward, con
     for (int o = 0; o < NOBJ; o++) { const double* p = st + 18 + 13 * o; ob[o].pos = mk<T>((T)p[0], (T)p[1], (T)p[2]); ob[o].qx = (T)p[3]; ob[o].qy = (T)p[4]; ob[o].qz = (T)p[5]; ob[o].qw = (T)p[6]; ob[o].lin = mk<T>((T)p[7], (T)p[8], (T)p[9]); ob[o].ang = mk<T>((T)p[10], (T)p[11], (T)p[12]); }
     for (int k = 0; k < 6; k++) goal[k] = (T)st[44 + k];
     static Contacts<T> C; static T slab[solver_slots(2)]; C.st.base = slab; C.st.stride = 1;
-    int mc = 0; env_step<T, TASK, CTRL>(M, S, reward, q, qd, ob, goal, action, nullptr, obs, ag, dg, *rew, *succ, C, mc);
+    int mc = 0; T target[ND]; env_step<T, TASK, CTRL>(M, S, reward, q, qd, ob, goal, action, nullptr, obs, ag, dg, *rew, *succ, C, mc, target);
     for (int i = 0; i < ND; i++) { st[i] = q[i]; st[9 + i] = qd[i]; }
     for (int o = 0; o < NOBJ; o++) { double* p = st + 18 + 13 * o; p[0] = ob[o].pos.x; p[1] = ob[o].pos.y; p[2] = ob[o].pos.z; p[3] = ob[o].qx; p[4] = ob[o].qy; p[5] = ob[o].qz; p[6] = ob[o].qw; p[7] = ob[o].lin.x; p[8] = ob[o].lin.y; p[9] = ob[o].lin.z; p[10] = ob[o].ang.x; p[11] = ob[o].ang.y; p[12] = ob[o].ang.z; }
 }
@@ -65,6 +65,8 @@ template <typename T> static void env_step_d(int task, int ctrl, int reward, con
 extern "C" {
 long hc_dbg_fallbacks() { return pg::g_dbg_fallbacks; }
 long hc_dbg_full_starts() { return pg::g_dbg_full_starts; }
+int hc_dbg_trace(int* out) { int n = pg::g_dbg_ntrace; for (int i = 0; i < n; i++) out[i] = pg::g_dbg_trace[i]; pg::g_dbg_ntrace = 0; return n; }
+void hc_dbg_solver(long* out) { out[0] = pg::g_dbg_sweeps; out[1] = pg::g_dbg_solves; out[2] = pg::g_dbg_contacts; }
 void hc_env_step(int dbl, int task, int ctrl, int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
     if (dbl) env_step_d<double>(task, ctrl, reward, base, st, action, obs, ag, dg, rew, succ); else env_step_d<float>(task, ctrl, reward, base, st, action, obs, ag, dg, rew, succ);
 }
