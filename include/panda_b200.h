@@ -96,6 +96,9 @@ int pg_diverged(pg_env* env, long long* count);
  * the previous one (bits 0-4 contacts at the end of the launch, bit 5 robot contact, bit 6 solver ran all sweeps, bit 7 near a
  * contact, bit 9 full joint-limit sweep). */
 int pg_debug_schedule(pg_env* env, unsigned short* key, int* perm);
+/* Timing introspection (handles created with PG_DEBUG_TIMING=1 in the environment): per thread slot of the last launch, the SM
+ * cycles spent in the env's step code and the key it wrote; out is a host buffer of num_envs x 2 int64. */
+int pg_debug_timing(pg_env* env, long long* out);
 /* Number of kernels this library has launched in this process. */
 long long pg_kernel_launches(void);
 const char* pg_last_error(void);

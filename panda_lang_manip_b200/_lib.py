@@ -19,7 +19,7 @@ PRECISION = {"f32": 0, "f64": 1}
 SYMBOLS = [
     "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_compute_reward", "pg_is_success",
     "pg_compute_reward_host", "pg_is_success_host", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
-    "pg_inverse_kinematics", "pg_get_ee_pose", "pg_debug_schedule", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
+    "pg_inverse_kinematics", "pg_get_ee_pose", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
 _lib = None
@@ -64,6 +64,7 @@ def load() -> ctypes.CDLL:
     lib.pg_inverse_kinematics.argtypes = [vp, vp, vp, vp, vp]
     lib.pg_get_ee_pose.argtypes = [vp, vp, vp]
     lib.pg_debug_schedule.argtypes = [vp, vp, vp]
+    lib.pg_debug_timing.argtypes = [vp, vp]
     lib.pg_diverged.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     lib.pg_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.pg_kernel_launches.restype = c_ll

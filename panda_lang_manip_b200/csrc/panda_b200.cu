@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -68,7 +69,11 @@ struct pg_env {
     EnvDev<float> Ef; EnvDev<double> Ed;
     std::map<int, void*> snaps; int next_snap = 0;
     bool sort_envs = true;                            // PG_SORT_ENVS=0 disables the contact-aware thread->env map (A/B measurements)
-    int segments = 4;                                 // launches per step for sorted batches: 20 with objects, 4 without; PG_SEGMENTS overrides (a divisor of 20)
+    // env groups: sorted batches are cut into groups of consecutive envs, each advanced on its own stream, so that the tail of
+    // one group's launch (a few contact-heavy blocks) overlaps with the other groups' launches instead of idling the GPU
+    long long* dbg = nullptr;
+    int groups = 1; cudaStream_t gstream[8] = {}; cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+    int segments = 4;                                 // launches per step for sorted batches (see pg_create); PG_SEGMENTS overrides (a divisor of 20)
     // host-buffer path: pinned staging + device I/O buffers + private stream
     cudaStream_t hstream = nullptr;
     float *h_act = nullptr, *h_out = nullptr; float* d_act = nullptr; float* d_out = nullptr; size_t out_floats = 0; size_t out_bytes = 0;
@@ -86,7 +91,7 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.target = (T*)take(9 * n * sizeof(T));
     E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
     E.ccount = (unsigned short*)take(n * sizeof(unsigned short)); E.perm = (int*)take(n * sizeof(int));
-    E.hist = (int*)take(((n + PERM_CHUNK - 1) / PERM_CHUNK) * PERM_BUCKETS * sizeof(int));
+    E.hist = (int*)take(((n + PERM_CHUNK - 1) / PERM_CHUNK + 8) * PERM_BUCKETS * sizeof(int));
     e->blob_bytes = off;
 }
 
@@ -129,7 +134,18 @@ int pg_create(int task, int control_type, int reward_type, int num_envs, int dev
     if (precision == PG_F32) { bind(e->Ef, e, (char*)e->blob, seed, env_id_offset); e->Ef.M = make_model<float>(base); e->Ef.S = make_scene<float>(task); }
     else { bind(e->Ed, e, (char*)e->blob, seed, env_id_offset); e->Ed.M = make_model<double>(base); e->Ed.S = make_scene<double>(task); }
     { const char* v = getenv("PG_SORT_ENVS"); if (v && v[0] == '0') e->sort_envs = false; }
-    e->segments = e->nobj > 0 ? 20 : 4;
+    const bool light = e->nobj == 0 && control_type == CTRL_JOINTS;
+    e->segments = light ? 4 : 20;
+    { const char* v = getenv("PG_DEBUG_TIMING"); if (v && v[0] == '1') { PG_CUDA(cudaMalloc(&e->dbg, (size_t)e->n * 2 * sizeof(long long))); PG_CUDA(cudaMemset(e->dbg, 0, (size_t)e->n * 2 * sizeof(long long))); } }
+    e->Ef.dbg = e->dbg; e->Ed.dbg = e->dbg;
+    // measured defaults (profiles/r1_notes.md): contact scenes and ee control re-sort before every sub-step and run 4 env groups;
+    // joint-controlled Reach (few contacts) keeps 4 launches per step on one stream
+    e->groups = (num_envs >= 16384 && !light) ? 4 : 1;
+    { const char* v = getenv("PG_GROUPS"); if (v) { int k = atoi(v); if (k >= 1 && k <= 8) e->groups = k; } }
+    if (e->groups > 1) {
+        PG_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        for (int g = 0; g < e->groups; g++) { PG_CUDA(cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking)); PG_CUDA(cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming)); }
+    }
     { const char* v = getenv("PG_SEGMENTS"); if (v) { int k = atoi(v); if (k >= 1 && k <= 20 && 20 % k == 0) e->segments = k; } }
     *out = e;
     int rc = pg_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -147,6 +163,9 @@ int pg_destroy(pg_env* e) {
     if (e->d_act) cudaFree(e->d_act);
     if (e->d_out) cudaFree(e->d_out);
     if (e->hstream) cudaStreamDestroy(e->hstream);
+    for (int g = 0; g < 8; g++) { if (e->gstream[g]) cudaStreamDestroy(e->gstream[g]); if (e->ev_join[g]) cudaEventDestroy(e->ev_join[g]); }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->dbg) cudaFree(e->dbg);
     cudaFree(e->blob);
     delete e;
     return PG_OK;
@@ -192,15 +211,28 @@ int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, 
     int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
     EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
     if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
-    for (int sg = 0; sg < segs; sg++) {
-        StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset, sg * 20 / segs, (sg + 1) * 20 / segs};
-        if (use_perm) {
-            const int nchunks = (e->n + PERM_CHUNK - 1) / PERM_CHUNK;
-            perm_hist_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, e->n);
-            perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, (cudaStream_t)stream>>>(key, hist, perm, e->n, nchunks);
-            g_launches += 2;
+    const int groups = use_perm ? e->groups : 1;
+    // group g owns the envs (and thread slots) [g * gsize, min(n, (g + 1) * gsize)), gsize a multiple of the sort chunk
+    const int gsize = ((e->n + groups - 1) / groups + PERM_CHUNK - 1) / PERM_CHUNK * PERM_CHUNK;
+    if (groups > 1) PG_CUDA(cudaEventRecord(e->ev_fork, (cudaStream_t)stream));
+    for (int g = 0; g < groups; g++) {
+        const int t0 = g * gsize, cnt = std::min(e->n, t0 + gsize) - t0;
+        if (cnt <= 0) break;
+        cudaStream_t st = groups > 1 ? e->gstream[g] : (cudaStream_t)stream;
+        if (groups > 1) PG_CUDA(cudaStreamWaitEvent(st, e->ev_fork, 0));
+        Ef.t0 = Ed.t0 = t0; Ef.tcount = Ed.tcount = cnt;
+        const int nchunks = (cnt + PERM_CHUNK - 1) / PERM_CHUNK;
+        int* ghist = hist + (size_t)(t0 / PERM_CHUNK + g) * PERM_BUCKETS;
+        for (int sg = 0; sg < segs; sg++) {
+            StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset, sg * 20 / segs, (sg + 1) * 20 / segs};
+            if (use_perm) {
+                perm_hist_kernel<<<nchunks, PERM_THREADS, 0, st>>>(key + t0, ghist, cnt);
+                perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, st>>>(key + t0, ghist, perm + t0, cnt, nchunks, t0);
+                g_launches += 2;
+            }
+            if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, st); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, st);
         }
-        if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, (cudaStream_t)stream); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, (cudaStream_t)stream);
+        if (groups > 1) { PG_CUDA(cudaEventRecord(e->ev_join[g], st)); PG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_join[g], 0)); }
     }
     PG_CUDA(cudaGetLastError());
     return PG_OK;
@@ -351,6 +383,14 @@ int pg_debug_schedule(pg_env* e, unsigned short* key_host, int* perm_host) {
     PG_CUDA(cudaSetDevice(e->device));
     PG_CUDA(cudaMemcpy(key_host, e->precision == PG_F32 ? e->Ef.ccount : e->Ed.ccount, (size_t)e->n * sizeof(unsigned short), cudaMemcpyDeviceToHost));
     PG_CUDA(cudaMemcpy(perm_host, e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm, (size_t)e->n * sizeof(int), cudaMemcpyDeviceToHost));
+    return PG_OK;
+}
+int pg_debug_timing(pg_env* e, long long* out) {
+    if (!e || !out) return fail(PG_ERR_ARG, "pg_debug_timing: NULL argument");
+    if (!e->dbg) return fail(PG_ERR_ARG, "pg_debug_timing: create the handle with PG_DEBUG_TIMING=1 in the environment");
+    PG_CUDA(cudaSetDevice(e->device));
+    PG_CUDA(cudaDeviceSynchronize());
+    PG_CUDA(cudaMemcpy(out, e->dbg, (size_t)e->n * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
     return PG_OK;
 }
 int pg_diverged(pg_env* e, long long* count) {

@@ -413,39 +413,44 @@ PG_HD void rows_setup(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<
     }
 }
 
-// J . dv of a row along direction d
-template <typename T, int NOBJ>
-PG_HD T row_jdv(const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, V3<T> d, const T* w, const T* d8, const V3<T>* dvl, const V3<T>* dva, const Obj<T>* ob) {
-    T jd = T(0);
-    if (X.rb >= 0) jd += dot8(w, d8);
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) if (X.sgo[o] != T(0)) jd += X.sgo[o] * dot(d, dvl[o] + cross(dva[o], X.P - ob[o].pos));
-    return jd;
-}
-template <typename T, int NOBJ>
-PG_HD void row_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, V3<T> d, const T* w, T di,
-                     T* d8, T* F8, V3<T>* dvl, V3<T>* dva, const Obj<T>* ob) {
-    if (X.rb >= 0) {
-        T wi[8], y[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { wi[i] = w[i] * di; F8[i] += wi[i]; }
-        lambda_mul(Op, wi, y);
-#pragma unroll
-        for (int i = 0; i < 8; i++) d8[i] += y[i];
-    }
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) {
-        if (X.sgo[o] != T(0)) {
-            dvl[o] = dvl[o] + d * (X.sgo[o] * di / S.mass[o]);
-            dva[o] = dva[o] + sym6_mul(W.Iinv[o], cross(X.P - ob[o].pos, d)) * (X.sgo[o] * di);
-        }
-    }
-}
-
 #ifdef PG_HOST_DEBUG
 static long g_dbg_fallbacks = 0, g_dbg_full_starts = 0, g_dbg_sweeps = 0, g_dbg_solves = 0, g_dbg_contacts = 0;
 static int g_dbg_trace[4096], g_dbg_ntrace = 0;
 #endif
+// Generic rows (robot box <-> object, object <-> object) work on the relative velocity change at the contact point, body A minus
+// body B: u = s (v6 + w6 x r6 +- hy q'_finger) + sum_o sg_o (dv_o + dw_o x r_o).  J dv of a row along d is d . u (one u for the three
+// rows of a contact), and an impulse vector f (normal: n di; friction: t1 d1 + t2 d2, solved from the same state) is applied
+// with one Lambda product.
+template <typename T, int NOBJ>
+PG_HD V3<T> contact_dv(const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, const T* d8, const V3<T>* dvl, const V3<T>* dva, const Obj<T>* ob) {
+    V3<T> u = mk<T>(T(0), T(0), T(0));
+    if (X.rb >= 0) {
+        const T fs = X.rb == 1 ? d8[6] : (X.rb == 2 ? -d8[7] : T(0));
+        u = (mk<T>(d8[3], d8[4], d8[5]) + cross(mk<T>(d8[0], d8[1], d8[2]), X.P - Op.O6) + Op.hy * fs) * X.s;
+    }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) if (X.sgo[o] != T(0)) u = u + (dvl[o] + cross(dva[o], X.P - ob[o].pos)) * X.sgo[o];
+    return u;
+}
+template <typename T, int NOBJ>
+PG_HD void contact_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const ContactCtx<T, NOBJ>& X, V3<T> f,
+                         T* d8, T* F8, V3<T>* dvl, V3<T>* dva, const Obj<T>* ob) {
+    if (X.rb >= 0) {
+        T w[8], y[8];
+        robot_wrench<T, NOBJ>(Op, X, f, w);
+        lambda_mul(Op, w, y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { F8[i] += w[i]; d8[i] += y[i]; }
+    }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        if (X.sgo[o] != T(0)) {
+            dvl[o] = dvl[o] + f * (X.sgo[o] / S.mass[o]);
+            dva[o] = dva[o] + sym6_mul(W.Iinv[o], cross(X.P - ob[o].pos, f)) * X.sgo[o];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- full sub-step
 // One 2 ms stepSimulation: unconstrained velocities, contact generation at the current poses, <= 50 sequential-impulse sweeps
 // over [joint limits, motors] (direction alternating), contact normals, friction cones; exit when the largest squared
@@ -493,14 +498,12 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     C.f(c, C_APP) = sum;
                     row.apply(W.Iinv[o], T(1) / S.mass[o], di, dvl[o], dva[o]);
                 } else {
-                    T w[8];
-                    if (X.rb >= 0) robot_wrench<T, NOBJ>(Op, X, X.n, w);
-                    T jd = row_jdv<T, NOBJ>(Op, X, X.n, w, d8, dvl, dva, ob);
+                    T jd = dot(X.n, contact_dv<T, NOBJ>(Op, X, d8, dvl, dva, ob));
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - jd * inv;
                     T sum = app + di;
                     if (sum < T(0)) { di = -app; sum = T(0); }
                     C.f(c, C_APP) = sum;
-                    row_apply<T, NOBJ>(S, W, Op, X, X.n, w, di, d8, F8, dvl, dva, ob);
+                    contact_apply<T, NOBJ>(S, W, Op, X, X.n * di, d8, F8, dvl, dva, ob);
                 }
                 T r = div_fast(di, inv); res = fmax(res, r * r);
             }
@@ -544,16 +547,14 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     }
                 } else {
                     V3<T> t1, t2; plane_space(X.n, t1, t2);
-                    T w1[8], w2[8];
-                    if (X.rb >= 0) { robot_wrench<T, NOBJ>(Op, X, t1, w1); robot_wrench<T, NOBJ>(Op, X, t2, w2); }
-                    T j1 = row_jdv<T, NOBJ>(Op, X, t1, w1, d8, dvl, dva, ob), j2 = row_jdv<T, NOBJ>(Op, X, t2, w2, d8, dvl, dva, ob);
+                    const V3<T> u = contact_dv<T, NOBJ>(Op, X, d8, dvl, dva, ob);
+                    T j1 = dot(t1, u), j2 = dot(t2, u);
                     T s1 = a1 + C.f(c, C_RHS + 1) - j1 * i1, s2 = a2 + C.f(c, C_RHS + 2) - j2 * i2;
                     T len = sqrt(s1 * s1 + s2 * s2);
                     if (len > lim) { T f = div_fast(lim, len); s1 *= f; s2 *= f; }
                     d1 = s1 - a1; d2 = s2 - a2;
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
-                    row_apply<T, NOBJ>(S, W, Op, X, t1, w1, d1, d8, F8, dvl, dva, ob);
-                    row_apply<T, NOBJ>(S, W, Op, X, t2, w2, d2, d8, F8, dvl, dva, ob);
+                    contact_apply<T, NOBJ>(S, W, Op, X, t1 * d1 + t2 * d2, d8, F8, dvl, dva, ob);
                 }
                 T r1 = div_fast(d1, i1), r2 = div_fast(d2, i2);
                 res = fmax(res, fmax(r1 * r1, r2 * r2));

@@ -25,8 +25,10 @@ template <typename T> struct EnvDev {
     unsigned* episode;           // [n] episodes started (RNG counter)
     float* ret;                  // [n] running episode return
     double* stats;               // [5] episodes, successes, return sum, length sum, diverged envs
-    int* perm;                   // [n] thread -> env map of the next step (contact-heavy envs first), or NULL
+    int* perm;                   // [n] thread -> env map of the next launch (contact-heavy envs first), or NULL
+    int t0, tcount;              // sorted path: this launch covers the thread slots [t0, t0 + tcount) of perm (one env group)
     unsigned short* ccount;      // [n] scheduling key written by the env's last launch (see KEY_* in panda_env.cuh)
+    long long* dbg;              // [n][2] per-thread-slot (cycles spent in env_step, key) of the last launch, or NULL (PG_DEBUG_TIMING=1)
     int* hist;                   // [ceil(n/1024)][24] scratch of the bucket sort
     Model<T> M;
     Scene<T> S;
@@ -224,7 +226,8 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const un
 }
 // pass 2: bucket-major offsets (heaviest bucket first; chunks in order inside a bucket) and scatter.  The order inside one chunk's
 // slice of a bucket is arbitrary: the map only decides which thread runs which env, never a result.
-static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned short* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks) {
+// key / perm point at the group's first env / thread slot, id0 is that env's index
+static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned short* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks, int id0) {
     __shared__ int s_pos[PERM_BUCKETS], s_warp[PERM_THREADS / 32];
     // thread t owns bucket PERM_BUCKETS-1-t (descending order): total over all chunks, prefix over the chunks before this one
     const int b = PERM_BUCKETS - 1 - (int)threadIdx.x;
@@ -240,7 +243,7 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const
     if (b >= 0) s_pos[b] = carry + x - tot + pre;
     __syncthreads();
     const int base = blockIdx.x * PERM_CHUNK;
-    for (int i = base + threadIdx.x; i < min(n, base + PERM_CHUNK); i += PERM_THREADS) perm[atomicAdd(&s_pos[perm_bucket(key[i])], 1)] = i;
+    for (int i = base + threadIdx.x; i < min(n, base + PERM_CHUNK); i += PERM_THREADS) perm[atomicAdd(&s_pos[perm_bucket(key[i])], 1)] = id0 + i;
 }
 template <int W, typename E> __device__ __forceinline__ void row_load(const E* g, int i, E* reg) {
 #pragma unroll
@@ -267,10 +270,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
     float* s_io = reinterpret_cast<float*>(s_raw);
     __shared__ double s_stats[5];
     const long long row0 = (long long)blockIdx.x * BLOCK;
+    const bool mapped = E.perm != nullptr;               // launch-uniform
     const int t = (int)row0 + threadIdx.x;
-    const bool valid = t < E.n;
-    const bool mapped = E.perm != nullptr;               // block-uniform
-    const int i = (valid && mapped) ? E.perm[t] : t;
+    const bool valid = t < (mapped ? E.tcount : E.n);
+    const int i = (valid && mapped) ? E.perm[E.t0 + t] : t;
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0.0;
     const bool first = io.s0 == 0, last = io.s1 == 20;      // launch-uniform
     float act[NA];
@@ -289,8 +292,10 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
         int sched_key = E.ccount[i];                // in: KEY_FULL of the previous key; out: this launch's key
         float tquat[4];
         if (first && io.target_quat) row_load<4>(io.target_quat, i, tquat);
+        const long long clk0 = E.dbg ? clock64() : 0;
         env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, (first && io.target_quat) ? tquat : nullptr, obs, ag, dg, reward, term, C, sched_key,
                                 target, io.s0, io.s1);
+        if (E.dbg) { E.dbg[2 * (size_t)(E.t0 + t)] = clock64() - clk0; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); E.dbg[2 * (size_t)(E.t0 + t) + 1] = (long long)sched_key | ((long long)smid << 16); }
         if (last) {
             int steps = E.steps[i] + 1;
             trunc = steps >= task_max_steps(TASK);

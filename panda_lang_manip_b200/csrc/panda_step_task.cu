@@ -11,7 +11,7 @@ namespace pg {
 extern long long g_launches;
 
 template <typename T, int TASK> void launch_step(const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st) {
-    const int grid = (E.n + BLOCK - 1) / BLOCK;
+    const int grid = ((E.perm ? E.tcount : E.n) + BLOCK - 1) / BLOCK;
     static bool configured = false;
     if (!configured) {      // > 48 KB of dynamic shared memory needs the opt-in
         cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_EE>());
