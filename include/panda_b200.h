@@ -65,6 +65,14 @@ int pg_compute_reward(int task, int reward_type, const void* achieved_goal, cons
                       long long m, int dtype, void* stream);
 int pg_is_success(int task, const void* achieved_goal, const void* desired_goal, unsigned char* success, long long m,
                   int dtype, void* stream);
+/* HER relabelling fused with compute_reward (replaces the gather + env.compute_reward round trip of stable-baselines3's
+ * HerReplayBuffer that reference examples/train_push.py:1-12 sets up; rewards as tasks/<task>.py compute_reward).  next_achieved_goal and
+ * desired_goal are the replay buffer's [R, G] goal arrays (device); for each of the M sampled transitions j: the new goal is
+ * next_achieved_goal[goal_src[j]] (desired_goal[src[j]] when goal_src[j] < 0) and the reward is compute_reward(next_achieved_goal[src[j]],
+ * new goal).  Outputs: desired_goal_out [M, G], achieved_goal_out [M, G] (may be NULL), reward [M] float32. */
+int pg_her_relabel(int task, int reward_type, const void* next_achieved_goal, const void* desired_goal, const long long* src,
+                   const long long* goal_src, void* desired_goal_out, void* achieved_goal_out, float* reward, long long m, int dtype,
+                   void* stream);
 int pg_compute_reward_host(int task, int reward_type, const void* achieved_goal, const void* desired_goal, float* reward,
                            long long m, int dtype, int device);
 int pg_is_success_host(int task, const void* achieved_goal, const void* desired_goal, unsigned char* success, long long m,

@@ -18,7 +18,7 @@ PRECISION = {"f32": 0, "f64": 1}
 
 SYMBOLS = [
     "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_compute_reward", "pg_is_success",
-    "pg_compute_reward_host", "pg_is_success_host", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
+    "pg_compute_reward_host", "pg_is_success_host", "pg_her_relabel", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_get_ee_pose", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
@@ -56,6 +56,7 @@ def load() -> ctypes.CDLL:
     lib.pg_is_success.argtypes = [c_int, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_compute_reward_host.argtypes = [c_int, c_int, vp, vp, vp, c_ll, c_int, c_int]
     lib.pg_is_success_host.argtypes = [c_int, vp, vp, vp, c_ll, c_int, c_int]
+    lib.pg_her_relabel.argtypes = [c_int, c_int, vp, vp, vp, vp, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_save_state.argtypes = [vp, pi]
     lib.pg_restore_state.argtypes = [vp, c_int]
     lib.pg_remove_state.argtypes = [vp, c_int]

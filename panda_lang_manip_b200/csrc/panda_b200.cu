@@ -107,6 +107,17 @@ template <typename E, bool WANT_REWARD> static void launch_reward(int task, cons
     g_launches++;
 }
 
+template <typename E> static void launch_her(int task, const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
+                                             long long m, int reward_type, cudaStream_t st) {
+    const int grid = (int)std::min<long long>((m + 255) / 256, 148LL * 16);
+    switch (task) {     // goal layouts: 3-D position (thr 0.05), Stack 6-D (thr 0.1), Flip quaternion (thr 0.2)
+    case 4: her_relabel_kernel<E, 4><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, reward_type); break;
+    case 5: her_relabel_kernel<E, 5><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, reward_type); break;
+    default: her_relabel_kernel<E, 0><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, reward_type); break;
+    }
+    g_launches++;
+}
+
 extern "C" {
 
 const char* pg_last_error(void) { return g_err.c_str(); }
@@ -288,6 +299,16 @@ int pg_is_success(int task, const void* ag, const void* dg, unsigned char* succe
     if (task < 0 || task > 5 || !ag || !dg || !success || m < 0) return fail(PG_ERR_ARG, "pg_is_success: bad argument");
     if (dtype == PG_F32) launch_reward<float, false>(task, (const float*)ag, (const float*)dg, nullptr, success, m, 0, (cudaStream_t)stream);
     else launch_reward<double, false>(task, (const double*)ag, (const double*)dg, nullptr, success, m, 0, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+int pg_her_relabel(int task, int reward_type, const void* next_ag, const void* dg, const long long* src, const long long* goal_src, void* dg_out, void* ag_out,
+                   float* reward, long long m, int dtype, void* stream) {
+    if (m == 0) return PG_OK;
+    if (task < 0 || task > 5 || reward_type < 0 || reward_type > 1 || !next_ag || !dg || !src || !goal_src || !dg_out || !reward || m < 0)
+        return fail(PG_ERR_ARG, "pg_her_relabel: bad argument");
+    if (dtype == PG_F32) launch_her<float>(task, (const float*)next_ag, (const float*)dg, src, goal_src, (float*)dg_out, (float*)ag_out, reward, m, reward_type, (cudaStream_t)stream);
+    else launch_her<double>(task, (const double*)next_ag, (const double*)dg, src, goal_src, (double*)dg_out, (double*)ag_out, reward, m, reward_type, (cudaStream_t)stream);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

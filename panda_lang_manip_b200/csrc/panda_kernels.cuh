@@ -433,6 +433,31 @@ __global__ void __launch_bounds__(256) reward_kernel(const E* __restrict__ ag, c
     }
 }
 
+// HER relabelling fused with compute_reward -- the caller on the learner side of the step (reference: examples/train_push.py:1-12
+// hands the env to stable-baselines3's HerReplayBuffer, which gathers `next_achieved_goal` rows as new goals and calls
+// Task.compute_reward, tasks/*.py, on the relabelled batch).  For sampled transition j: the new desired goal is the next achieved
+// goal of transition goal_src[j] (a later step of the same episode under the "future" strategy), or the stored desired goal when
+// goal_src[j] < 0; the reward is recomputed from the transition's own next achieved goal and the new goal, in the reference's
+// float32 arithmetic.  One thread per sampled transition; row gathers (12-24 B rows), 56 / 92 algorithmic bytes per transition.
+template <typename E, int TASK>
+__global__ void __launch_bounds__(256) her_relabel_kernel(const E* __restrict__ next_ag, const E* __restrict__ dg, const long long* __restrict__ src,
+                                                          const long long* __restrict__ goal_src, E* __restrict__ dg_out, E* __restrict__ ag_out,
+                                                          float* __restrict__ reward, long long m, int reward_type) {
+    constexpr int G = task_goal_dim(TASK);
+    const E thr = sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK);
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+        const long long s = src[j], gs = goal_src[j];
+        const E* pg = gs >= 0 ? next_ag + gs * G : dg + s * G;
+        E a[G], b[G];
+#pragma unroll
+        for (int k = 0; k < G; k++) { a[k] = next_ag[s * G + k]; b[k] = pg[k]; }
+        E d = goal_distance(TASK, a, b);
+        reward[j] = reward_from_distance(reward_type, d, thr);
+#pragma unroll
+        for (int k = 0; k < G; k++) { dg_out[j * G + k] = b[k]; if (ag_out) ag_out[j * G + k] = a[k]; }
+    }
+}
+
 // host-side launchers, instantiated per task in panda_step_task.cu
 template <typename T, int TASK> void launch_step(const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st);
 template <typename T, int TASK> void launch_reset(const EnvDev<T>& E, const ResetIO& io, cudaStream_t st);

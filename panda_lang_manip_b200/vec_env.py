@@ -126,6 +126,35 @@ class PandaVecEnv:
     def remove_state(self, state_id: int) -> None:
         _lib.check(self.lib.pg_remove_state(self._h, int(state_id)))
 
+    def lookahead(self, candidate_actions: torch.Tensor, commit: bool = True):
+        """Batched greedy look-ahead search (reference docs/usage/save_restore_state.rst:8-41: save_state, try K sampled actions
+        from the same state, keep the one with the best reward): ``candidate_actions`` is [K, N, A]; every env evaluates its K
+        candidates from the current state (one snapshot, K restored steps without auto-reset) and, with ``commit``, is then stepped
+        with its own best action.  Returns (best_action [N, A], best_reward [N], step result or None).  Ties keep the first candidate."""
+        c = candidate_actions.to(device=self.device, dtype=torch.float32)
+        if c.dim() != 3 or c.shape[1:] != (self.num_envs, self.action_dim):
+            raise ValueError(f"candidate_actions must be [K, {self.num_envs}, {self.action_dim}], got {tuple(c.shape)}")
+        sid = self.save_state()
+        keep = self.auto_reset
+        self.auto_reset = False                      # a candidate that ends the episode must not restart it
+        best_r = torch.full((self.num_envs,), -float("inf"), dtype=torch.float32, device=self.device)
+        best_k = torch.zeros((self.num_envs,), dtype=torch.long, device=self.device)
+        try:
+            for k in range(c.shape[0]):
+                if k > 0:
+                    self.restore_state(sid)
+                _, r, _, _, _ = self.step(c[k])
+                better = r > best_r
+                best_r = torch.where(better, r, best_r)
+                best_k = torch.where(better, torch.full_like(best_k, k), best_k)
+        finally:
+            self.auto_reset = keep
+            self.restore_state(sid)
+            self.remove_state(sid)
+        best_a = c.gather(0, best_k.view(1, -1, 1).expand(1, self.num_envs, self.action_dim))[0].contiguous()
+        out = self.step(best_a) if commit else None
+        return best_a, best_r, out
+
     def get_state(self) -> torch.Tensor:
         """[N, state_dim] float64: q(9) qd(9) | per object pos3 quat4 lin3 ang3 | goal | episode step."""
         s = torch.empty((self.num_envs, self.state_dim), dtype=torch.float64, device=self.device)
@@ -195,3 +224,45 @@ def is_success(task: str, achieved_goal: torch.Tensor, desired_goal: torch.Tenso
     with torch.cuda.device(a.device):
         _lib.check(_lib.load().pg_is_success(_lib.TASKS[task], _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
     return out.bool()
+
+
+def her_relabel(task: str, reward_type: str, next_achieved_goal: torch.Tensor, desired_goal: torch.Tensor, src: torch.Tensor, goal_src: torch.Tensor,
+                return_achieved: bool = False):
+    """HER relabelling fused with compute_reward, on the device (the learner-side caller of the step path: the reference's
+    examples/train_push.py:1-12 sets up stable-baselines3's HerReplayBuffer, which does this with a numpy gather and
+    ``env.compute_reward``).  ``next_achieved_goal`` / ``desired_goal`` are the replay buffer's goal arrays flattened to [R, G];
+    ``src`` [M] indexes the sampled transitions and ``goal_src`` [M] the transitions whose next achieved goal becomes the new goal
+    (negative: keep the stored goal).  Returns (new_desired_goal [M, G], reward [M] float32[, next_achieved_goal[src] [M, G]])."""
+    if not (torch.is_tensor(next_achieved_goal) and next_achieved_goal.is_cuda):
+        raise _lib.PandaB200Error("her_relabel takes CUDA tensors: the replay buffer lives in HBM")
+    g = {"stack": 6, "flip": 4}.get(task, 3)
+    dt = torch.float64 if next_achieved_goal.dtype == torch.float64 else torch.float32
+    a = next_achieved_goal.to(dt).reshape(-1, g).contiguous()
+    d = desired_goal.to(device=a.device, dtype=dt).reshape(-1, g).contiguous()
+    if a.shape != d.shape:
+        raise ValueError("next_achieved_goal and desired_goal must have the same [R, G] shape")
+    s_ = src.to(device=a.device, dtype=torch.long).contiguous()
+    gs = goal_src.to(device=a.device, dtype=torch.long).contiguous()
+    if s_.shape != gs.shape or s_.dim() != 1:
+        raise ValueError("src and goal_src must be 1-D and of equal length")
+    m = s_.numel()
+    new_dg = torch.empty((m, g), dtype=dt, device=a.device)
+    ag_out = torch.empty((m, g), dtype=dt, device=a.device) if return_achieved else None
+    rew = torch.empty((m,), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().pg_her_relabel(_lib.TASKS[task], _lib.REWARD[reward_type], _ptr(a), _ptr(d), _ptr(s_), _ptr(gs), _ptr(new_dg), _ptr(ag_out), _ptr(rew),
+                                              m, 1 if dt == torch.float64 else 0, torch.cuda.current_stream(a.device).cuda_stream))
+    return (new_dg, rew, ag_out) if return_achieved else (new_dg, rew)
+
+
+def future_goal_indices(episode_start: torch.Tensor, episode_length: torch.Tensor, src: torch.Tensor, her_ratio: float = 0.8,
+                        generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """The "future" goal-selection strategy of HER for ``her_relabel``: transition ``src[j]`` belongs to an episode stored in the
+    flat rows [episode_start[j], episode_start[j] + episode_length[j]); with probability ``her_ratio`` pick a row uniformly from
+    the transition's own row to the episode's last row, else -1 (keep the stored goal)."""
+    off = src - episode_start
+    span = (episode_length - off).clamp_min(1)
+    u = torch.rand(src.shape, device=src.device, generator=generator)
+    fut = src + (u * span).long().clamp_max(span - 1)
+    keep = torch.rand(src.shape, device=src.device, generator=generator) >= her_ratio
+    return torch.where(keep, torch.full_like(fut, -1), fut)
