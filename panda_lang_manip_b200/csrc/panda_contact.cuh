@@ -625,7 +625,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
         W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
     }
     JointRows<T> R;
-    joint_rows_setup(M, q, qd, target, Minv, R);
+    joint_rows_setup<WATCH_LIMITS>(M, q, qd, target, Minv, R);
     collect_contacts<T, NOBJ>(S, W, ob, C);
     OpSpace<T> Op;
     const bool robot_contacts = C.nr > 0;

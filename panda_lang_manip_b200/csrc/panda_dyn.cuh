@@ -466,7 +466,19 @@ template <typename T> struct JointRows {
     T mot_rhs[ND], mot_app[ND];
     T invD[ND];
 };
-template <typename T> PG_HD void joint_rows_setup(const Model<T>& M, const T* q, const T* qd, const T* target, const T (*Minv)[ND], JointRows<T>& R) {
+// Keeps a value in its register: without it the compiler rematerialises the 27 row right-hand sides from q, qd and the targets
+// inside every sweep (~5 extra instructions per row and sweep, seen in the SASS of the sweep loop).
+PG_HD void pin(float& x) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+f"(x));
+#endif
+}
+PG_HD void pin(double& x) {
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(x));
+#endif
+}
+template <bool PIN = false, typename T> PG_HD void joint_rows_setup(const Model<T>& M, const T* q, const T* qd, const T* target, const T (*Minv)[ND], JointRows<T>& R) {
     const T inv_dt = Consts<T>::inv_dt;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
@@ -481,14 +493,16 @@ template <typename T> PG_HD void joint_rows_setup(const Model<T>& M, const T* q,
         // POSITION_CONTROL, kp = 0.1, kd = 1, target velocity 0: desired velocity 0.1 (q* - q)/dt
         T vt = T(0.1) * (target[d] - q[d]) * inv_dt;
         R.mot_rhs[d] = (vt - qd[d]) * invD; R.mot_app[d] = T(0);
+        if (PIN) { pin(R.lim_rhs[2 * d]); pin(R.lim_rhs[2 * d + 1]); pin(R.mot_rhs[d]); }   // measured: +10 % with the watched-limit sweep, -2 % with the full one
     }
 }
 template <int D, int SIDE, typename T> PG_HD void limit_row(const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
     const T sg = SIDE == 0 ? T(1) : T(-1);
     T di = R.lim_rhs[2 * D + SIDE] - sg * dv[D] * R.invD[D];
     T app = R.lim_app[2 * D + SIDE], sum = app + di;
-    if (sum < T(0)) { di = -app; sum = T(0); } else if (sum > T(100)) { di = T(100) - app; sum = T(100); }
-    R.lim_app[2 * D + SIDE] = sum;
+    const T sumc = fmin(fmax(sum, T(0)), T(100));       // impulse in [0, 100]; di is only recomputed when the clamp acts (same values, 3 instructions less)
+    di = sumc != sum ? sumc - app : di;
+    R.lim_app[2 * D + SIDE] = sumc;
     T w = sg * di;
 #pragma unroll
     for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * w;
@@ -497,8 +511,9 @@ template <int D, int SIDE, typename T> PG_HD void limit_row(const T (*Minv)[ND],
 template <int D, typename T> PG_HD void motor_row(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
     T di = R.mot_rhs[D] - dv[D] * R.invD[D];
     T app = R.mot_app[D], sum = app + di, mx = M.max_imp[D];
-    if (sum < -mx) { di = -mx - app; sum = -mx; } else if (sum > mx) { di = mx - app; sum = mx; }
-    R.mot_app[D] = sum;
+    const T sumc = fmin(fmax(sum, -mx), mx);
+    di = sumc != sum ? sumc - app : di;
+    R.mot_app[D] = sumc;
 #pragma unroll
     for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * di;
     T r = di * Minv[D][D]; res = fmax(res, r * r);
