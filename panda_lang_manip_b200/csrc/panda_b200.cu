@@ -149,9 +149,9 @@ int pg_create(int task, int control_type, int reward_type, int num_envs, int dev
     e->segments = light ? 4 : 20;
     { const char* v = getenv("PG_DEBUG_TIMING"); if (v && v[0] == '1') { PG_CUDA(cudaMalloc(&e->dbg, (size_t)e->n * 2 * sizeof(long long))); PG_CUDA(cudaMemset(e->dbg, 0, (size_t)e->n * 2 * sizeof(long long))); } }
     e->Ef.dbg = e->dbg; e->Ed.dbg = e->dbg;
-    // measured defaults (profiles/r1_notes.md): contact scenes and ee control re-sort before every sub-step and run 4 env groups;
+    // measured defaults (profiles/r1_notes.md): contact scenes and ee control re-sort before every sub-step and run 4 env groups (2 for ee-controlled Reach);
     // joint-controlled Reach (few contacts) keeps 4 launches per step on one stream
-    e->groups = (num_envs >= 16384 && !light) ? 4 : 1;
+    e->groups = (num_envs >= 16384 && !light) ? (e->nobj == 0 ? 2 : 4) : 1;
     { const char* v = getenv("PG_GROUPS"); if (v) { int k = atoi(v); if (k >= 1 && k <= 8) e->groups = k; } }
     if (e->groups > 1) {
         PG_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
