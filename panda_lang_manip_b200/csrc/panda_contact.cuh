@@ -639,7 +639,8 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
     // Arm limit rows are exact no-ops while they rest at zero impulse: the fast solve only watches them and, if one would engage,
-    // the solve restarts from zero impulses with every row real (bit-identical to always running the full sweep).
+    // the solve restarts from zero impulses with every row real (a watched row is an exact no-op: the result is the full sweep's, up to
+    // FMA-contraction differences between the two loop instantiations).
     const int nc = C.n;
     bool fast = WATCH_LIMITS && !full_sweep && !arm_limit_violated(M, q);
 #ifdef PG_HOST_DEBUG
