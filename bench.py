@@ -24,9 +24,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec"
-# dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch from the committed `ncu --set full` capture
-# (profiles/r1_step_kernel_ncu_full_raw.csv); None where no capture exists for the configuration
-NCU_TRAFFIC = {("reach", "joints", 65536): 8390912}
+# dram__bytes_read.sum + dram__bytes_write.sum per env-step call = per step_kernel launch (committed `ncu --set full` captures,
+# profiles/r1_step_kernel*_ncu_full_raw.csv; ncu flushes the caches before every replay pass, so these are cold-cache figures) x the
+# step_kernel launches one step is cut into; None where no capture exists for the configuration
+NCU_TRAFFIC = {("reach", "joints", 65536): 4 * 8396032, ("pick_and_place", "ee", 32768): 80 * 1758720}
+STEP_LAUNCHES = {("reach", "joints", 65536): "4 launches of 5 sub-steps (512 blocks)", ("pick_and_place", "ee", 32768): "4 env groups x 20 launches of 1 sub-step (64 blocks)"}
 ENV_IDS = {"reach": "PandaReach", "push": "PandaPush", "slide": "PandaSlide", "pick_and_place": "PandaPickAndPlace", "stack": "PandaStack", "flip": "PandaFlip"}
 TASK_ID = {"reach": 0, "push": 1, "slide": 2, "pick_and_place": 3, "stack": 4, "flip": 5}
 # algorithmic bytes per env-step, fp32 SoA: read state+goal+action, write state+obs+ag+dg+reward+2 flags
@@ -258,7 +260,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "pg_step_host (C ABI, host buffers)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.task, args.control, n)),
-                         "kernel": "step_kernel", "bytes_per_env_step": bps, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "kernel": "step_kernel", "launches_per_step": STEP_LAUNCHES.get((args.task, args.control, n)), "bytes_per_env_step": bps, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "latency/issue-bound kernel (~1 MFLOP of serial dynamics per env-step): the HBM fraction is structurally tiny, see DESIGN.md"},
             "her_compute_reward": her,
             "clocks": clocks,

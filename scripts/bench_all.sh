@@ -10,4 +10,6 @@ for t in push slide stack flip; do
 done
 timeout 300 python bench.py --envs 262144 --no-cpu --no-her > gpurun_out/bench_${TAG}_reach_joints_262144.json 2>> gpurun_out/bench_${TAG}.err
 timeout 300 python bench.py --task pick_and_place --control ee --envs 131072 --no-cpu --no-her > gpurun_out/bench_${TAG}_pnp_131072.json 2>> gpurun_out/bench_${TAG}.err
+timeout 300 python bench.py --control ee --envs 262144 --no-cpu --no-her > gpurun_out/bench_${TAG}_reach_ee_262144.json 2>> gpurun_out/bench_${TAG}.err
+timeout 300 python bench.py --reward dense --no-cpu --no-her > gpurun_out/bench_${TAG}_reach_joints_dense.json 2>> gpurun_out/bench_${TAG}.err
 tail -3 gpurun_out/pytest_gpu_$TAG.log
