@@ -508,6 +508,28 @@ template <int D, int SIDE, typename T> PG_HD void limit_row(const T (*Minv)[ND],
     for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * w;
     T r = di * Minv[D][D]; res = fmax(res, r * r);
 }
+// Both limit rows of joint D, side FIRST then the other.  The same values as two limit_row calls: the joint's own velocity is updated
+// after each row (the second row reads it), the other eight joints get the two impulse changes at once -- at most one row of a
+// pair carries impulse, the other's change is exactly zero, so the sum is that one change.  Saves 8 FMAs per joint and sweep.
+template <int D, int FIRST, typename T> PG_HD void limit_pair(const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
+    T w = T(0);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int side = h == 0 ? FIRST : 1 - FIRST;
+        const T sg = side == 0 ? T(1) : T(-1);
+        T di = R.lim_rhs[2 * D + side] - sg * dv[D] * R.invD[D];
+        T app = R.lim_app[2 * D + side], sum = app + di;
+        const T sumc = fmin(fmax(sum, T(0)), T(100));
+        di = sumc != sum ? sumc - app : di;
+        R.lim_app[2 * D + side] = sumc;
+        const T wi = sg * di;
+        dv[D] += Minv[D][D] * wi;
+        w += wi;
+        T r = di * Minv[D][D]; res = fmax(res, r * r);
+    }
+#pragma unroll
+    for (int k = 0; k < ND; k++) if (k != D) dv[k] += Minv[k][D] * w;
+}
 template <int D, typename T> PG_HD void motor_row(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
     T di = R.mot_rhs[D] - dv[D] * R.invD[D];
     T app = R.mot_app[D], sum = app + di, mx = M.max_imp[D];
@@ -531,7 +553,7 @@ template <int D, bool FAST, typename T> struct RowsFwd {
     static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, bool& live) {
         RowsFwd<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
         if (FAST && D < 7) { limit_watch<D, 0>(R, dv, live); limit_watch<D, 1>(R, dv, live); }
-        else { limit_row<D, 0>(Mi, R, dv, res); limit_row<D, 1>(Mi, R, dv, res); }
+        else limit_pair<D, 0>(Mi, R, dv, res);
     }
     static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, FAST, T>::mot(M, Mi, R, dv, res); motor_row<D>(M, Mi, R, dv, res); }
 };
@@ -542,7 +564,7 @@ template <bool FAST, typename T> struct RowsFwd<-1, FAST, T> {
 template <int D, bool FAST, typename T> struct RowsRev {
     static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, bool& live) {
         if (FAST && D < 7) { limit_watch<D, 1>(R, dv, live); limit_watch<D, 0>(R, dv, live); }
-        else { limit_row<D, 1>(Mi, R, dv, res); limit_row<D, 0>(Mi, R, dv, res); }
+        else limit_pair<D, 1>(Mi, R, dv, res);
         RowsRev<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
     }
     static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { motor_row<D>(M, Mi, R, dv, res); RowsRev<D - 1, FAST, T>::mot(M, Mi, R, dv, res); }
