@@ -192,7 +192,7 @@ def run_gpu(args):
 
     # end to end through the C ABI with host buffers (H2D + kernel + D2H per step)
     e2e_steps = max(3, min(args.steps, 50))
-    host_actions = [np.ascontiguousarray(actions[i].cpu().numpy()) for i in range(ncyc)]
+    host_actions = [env.pin_host(np.ascontiguousarray(actions[i].cpu().numpy())) for i in range(ncyc)]     # pinned host inputs (the e2e contract)
     env.step_host(host_actions[0])
     barrier()
     t0 = time.perf_counter()

@@ -59,6 +59,11 @@ int pg_set_action_scale(pg_env* env, double ee_scale, double finger_scale);
 int pg_step_host(pg_env* env, const float* actions, float* obs, float* achieved_goal, float* desired_goal, float* reward,
                  unsigned char* terminated, unsigned char* truncated, int auto_reset);
 
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so that pg_step_host copies to / from it directly instead of through the
+ * handle's staging slabs; unpin before freeing the buffer.  Buffers that are not pinned work too (one extra host copy). */
+int pg_host_pin(void* ptr, size_t bytes);
+int pg_host_unpin(void* ptr);
+
 /* Task.compute_reward / Task.is_success (tasks/<task>.py, utils.py:4-30) on M rows of achieved/desired goals
  * (dtype PG_F32 or PG_F64 inputs; float32 rewards, uint8 success) -- the HER relabelling entry point. */
 int pg_compute_reward(int task, int reward_type, const void* achieved_goal, const void* desired_goal, float* reward,

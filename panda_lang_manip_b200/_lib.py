@@ -17,7 +17,7 @@ REWARD = {"sparse": 0, "dense": 1}
 PRECISION = {"f32": 0, "f64": 1}
 
 SYMBOLS = [
-    "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_compute_reward", "pg_is_success",
+    "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_host_pin", "pg_host_unpin", "pg_compute_reward", "pg_is_success",
     "pg_compute_reward_host", "pg_is_success_host", "pg_her_relabel", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_get_ee_pose", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
@@ -52,6 +52,8 @@ def load() -> ctypes.CDLL:
     lib.pg_step_oriented.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, c_int, vp]
     lib.pg_set_action_scale.argtypes = [vp, ctypes.c_double, ctypes.c_double]
     lib.pg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, c_int]
+    lib.pg_host_pin.argtypes = [vp, ctypes.c_size_t]
+    lib.pg_host_unpin.argtypes = [vp]
     lib.pg_compute_reward.argtypes = [c_int, c_int, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_is_success.argtypes = [c_int, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_compute_reward_host.argtypes = [c_int, c_int, vp, vp, vp, c_ll, c_int, c_int]

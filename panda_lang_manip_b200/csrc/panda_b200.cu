@@ -263,26 +263,46 @@ static int ensure_host_path(pg_env* e) {
     return PG_OK;
 }
 
+// page-locked (cudaHostAlloc / cudaHostRegister / pg_host_pin) host memory can be the source / target of an async copy directly
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+int pg_host_pin(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(PG_ERR_ARG, "pg_host_pin: bad argument");
+    PG_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return PG_OK;
+}
+int pg_host_unpin(void* ptr) {
+    if (!ptr) return fail(PG_ERR_ARG, "pg_host_unpin: NULL");
+    PG_CUDA(cudaHostUnregister(ptr));
+    return PG_OK;
+}
+
 int pg_step_host(pg_env* e, const float* actions, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated, unsigned char* truncated, int auto_reset) {
     if (!e || !actions) return fail(PG_ERR_ARG, "pg_step_host: NULL handle or actions");
     PG_CUDA(cudaSetDevice(e->device));
     int rc = ensure_host_path(e); if (rc != PG_OK) return rc;
     const size_t n = (size_t)e->n, O = e->obs_dim, G = e->goal_dim;
-    memcpy(e->h_act, actions, n * e->act_dim * sizeof(float));
-    PG_CUDA(cudaMemcpyAsync(e->d_act, e->h_act, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, e->hstream));
+    // pageable buffers go through the handle's pinned staging slabs (one extra host copy each way); pinned ones are copied directly
+    const float* src = actions;
+    if (!host_pinned(actions)) { memcpy(e->h_act, actions, n * e->act_dim * sizeof(float)); src = e->h_act; }
+    PG_CUDA(cudaMemcpyAsync(e->d_act, src, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, e->hstream));
     float* d_obs = e->d_out; float* d_ag = d_obs + n * O; float* d_dg = d_ag + n * G; float* d_rew = d_dg + n * G;
     unsigned char* d_term = (unsigned char*)(d_rew + n); unsigned char* d_trunc = d_term + n;
     rc = pg_step(e, e->d_act, d_obs, d_ag, d_dg, d_rew, d_term, d_trunc, auto_reset, e->hstream); if (rc != PG_OK) return rc;
-    PG_CUDA(cudaMemcpyAsync(e->h_out, e->d_out, e->out_bytes, cudaMemcpyDeviceToHost, e->hstream));
+    struct Out { void* user; const void* dev; size_t off, bytes; bool direct; };
+    Out outs[6] = {{obs, d_obs, 0, n * O * sizeof(float), false}, {ag, d_ag, 0, n * G * sizeof(float), false}, {dg, d_dg, 0, n * G * sizeof(float), false},
+                   {reward, d_rew, 0, n * sizeof(float), false}, {terminated, d_term, 0, n, false}, {truncated, d_trunc, 0, n, false}};
+    for (Out& o : outs) {
+        o.off = (size_t)((const char*)o.dev - (const char*)e->d_out);
+        if (!o.user) continue;
+        o.direct = host_pinned(o.user);
+        PG_CUDA(cudaMemcpyAsync(o.direct ? o.user : (void*)((char*)e->h_out + o.off), o.dev, o.bytes, cudaMemcpyDeviceToHost, e->hstream));
+    }
     PG_CUDA(cudaStreamSynchronize(e->hstream));
-    const float* h = e->h_out;
-    if (obs) memcpy(obs, h, n * O * sizeof(float));
-    if (ag) memcpy(ag, h + n * O, n * G * sizeof(float));
-    if (dg) memcpy(dg, h + n * O + n * G, n * G * sizeof(float));
-    if (reward) memcpy(reward, h + n * O + 2 * n * G, n * sizeof(float));
-    const unsigned char* hf = (const unsigned char*)(h + n * O + 2 * n * G + n);
-    if (terminated) memcpy(terminated, hf, n);
-    if (truncated) memcpy(truncated, hf + n, n);
+    for (const Out& o : outs) if (o.user && !o.direct) memcpy(o.user, (const char*)e->h_out + o.off, o.bytes);
     return PG_OK;
 }
 

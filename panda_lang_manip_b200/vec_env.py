@@ -39,6 +39,7 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_create(_lib.TASKS[task], _lib.CONTROL[control_type], _lib.REWARD[reward_type], self.num_envs, self.device_index,
                                       int(seed) & (2**64 - 1), int(env_id_offset), _lib.PRECISION[precision], ctypes.byref(h)))
         self._h = h
+        self._pinned = {}
         d = [ctypes.c_int() for _ in range(5)]
         _lib.check(self.lib.pg_dims(h, *[ctypes.byref(x) for x in d]))
         self.obs_dim, self.goal_dim, self.action_dim, self.max_episode_steps, self.state_dim = [x.value for x in d]
@@ -52,7 +53,23 @@ class PandaVecEnv:
         self.reset()
 
     # -- lifecycle ---------------------------------------------------------------------------------------------------
+    def pin_host(self, array: np.ndarray) -> np.ndarray:
+        """Page-lock a caller-owned numpy array (e.g. a reusable action buffer) so that ``step_host`` copies from / to it directly;
+        it is unpinned when the env is closed (or with ``unpin_host``).  Keep the array alive until then."""
+        a = np.ascontiguousarray(array)
+        if a.ctypes.data not in self._pinned:
+            _lib.check(self.lib.pg_host_pin(a.ctypes.data, a.nbytes))
+            self._pinned[a.ctypes.data] = a
+        return a
+
+    def unpin_host(self, array: np.ndarray) -> None:
+        if self._pinned.pop(array.ctypes.data, None) is not None:
+            _lib.check(self.lib.pg_host_unpin(array.ctypes.data))
+
     def close(self) -> None:
+        for ptr in list(getattr(self, "_pinned", {})):
+            self.lib.pg_host_unpin(ptr)
+            self._pinned.pop(ptr, None)
         if getattr(self, "_h", None) is not None:
             self.lib.pg_destroy(self._h)
             self._h = None
@@ -100,6 +117,8 @@ class PandaVecEnv:
         if not hasattr(self, "_host"):
             self._host = dict(obs=np.empty((n, self.obs_dim), np.float32), ag=np.empty((n, self.goal_dim), np.float32), dg=np.empty((n, self.goal_dim), np.float32),
                               rew=np.empty(n, np.float32), term=np.empty(n, np.uint8), trunc=np.empty(n, np.uint8))
+            for v in self._host.values():           # the env owns its output arrays: page-lock them, the D2H copies land in them directly
+                self.pin_host(v)
         hb = self._host
         _lib.check(self.lib.pg_step_host(self._h, a.ctypes.data, hb["obs"].ctypes.data, hb["ag"].ctypes.data, hb["dg"].ctypes.data, hb["rew"].ctypes.data,
                                          hb["term"].ctypes.data, hb["trunc"].ctypes.data, int(self.auto_reset)))

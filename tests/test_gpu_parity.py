@@ -310,3 +310,32 @@ def test_scheduling_is_invisible(task, ctrl):
         assert torch.equal(tb[k0:k0 + k], ts) and torch.equal(ub[k0:k0 + k], us)
     assert torch.equal(big.get_state()[k0:k0 + k], small.get_state())
     big.close(); small.close()
+
+
+@pytest.mark.gpu
+def test_host_path_pinned_and_pageable_buffers_agree():
+    """pg_step_host copies directly from / to page-locked buffers (pg_host_pin) and through its staging slabs otherwise: same results."""
+    import panda_lang_manip_b200 as p
+    n = 300
+    a_env = p.PandaVecEnv("push", n, seed=4, auto_reset=False)
+    b_env = p.PandaVecEnv("push", n, seed=4, auto_reset=False)
+    rng = np.random.default_rng(0)
+    pinned = a_env.pin_host(np.zeros((n, 3), np.float32))
+    for t in range(3):
+        act = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        pinned[:] = act
+        oa, ra, ta, ua, _ = a_env.step_host(pinned)
+        ob, rb, tb, ub, _ = b_env.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(oa["observation"], ob["observation"].cpu().numpy()) and np.array_equal(oa["desired_goal"], ob["desired_goal"].cpu().numpy())
+        assert np.array_equal(ra, rb.cpu().numpy()) and np.array_equal(ta, tb.cpu().numpy())
+    # the raw entry point with pageable outputs (staging slabs) on a third twin
+    c_env = p.PandaVecEnv("push", n, seed=4, auto_reset=False)
+    rng = np.random.default_rng(0)
+    o2, g2, d2, r2, t2, u2 = np.empty((n, 18), np.float32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8), np.empty(n, np.uint8)
+    for t in range(3):
+        act = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        rc = c_env.lib.pg_step_host(c_env._h, act.ctypes.data, o2.ctypes.data, g2.ctypes.data, d2.ctypes.data, r2.ctypes.data, t2.ctypes.data, u2.ctypes.data, 0)
+        assert rc == 0
+    assert np.array_equal(o2, oa["observation"]) and np.array_equal(r2, ra) and np.array_equal(t2, ta)
+    a_env.unpin_host(pinned)
+    a_env.close(); b_env.close(); c_env.close()
