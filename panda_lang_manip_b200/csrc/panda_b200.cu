@@ -365,7 +365,9 @@ int pg_save_state(pg_env* e, int* state_id) {
     PG_CUDA(cudaSetDevice(e->device));
     void* p = nullptr;
     PG_CUDA(cudaMalloc(&p, e->blob_bytes));
+    PG_CUDA(cudaDeviceSynchronize());       // steps may be in flight on the caller's stream and the group streams
     PG_CUDA(cudaMemcpy(p, e->blob, e->blob_bytes, cudaMemcpyDeviceToDevice));
+    PG_CUDA(cudaDeviceSynchronize());
     *state_id = e->next_snap++; e->snaps[*state_id] = p;
     return PG_OK;
 }
@@ -374,7 +376,9 @@ int pg_restore_state(pg_env* e, int state_id) {
     auto it = e->snaps.find(state_id);
     if (it == e->snaps.end()) return fail(PG_ERR_STATE, "pg_restore_state: unknown state id " + std::to_string(state_id));
     PG_CUDA(cudaSetDevice(e->device));
+    PG_CUDA(cudaDeviceSynchronize());
     PG_CUDA(cudaMemcpy(e->blob, it->second, e->blob_bytes, cudaMemcpyDeviceToDevice));
+    PG_CUDA(cudaDeviceSynchronize());
     return PG_OK;
 }
 int pg_remove_state(pg_env* e, int state_id) {
