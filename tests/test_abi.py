@@ -51,3 +51,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(d, f), errors="ignore").read()
                 assert "libpanda_oracle" not in src and "oracle_util" not in src and "panda_oracle.h" not in src, os.path.join(d, f)
+
+
+def test_learner_side_helpers_import_and_sample_on_cpu():
+    """adapters import without gymnasium / stable-baselines3 and without a GPU; the HER index sampler is plain torch (CPU here)."""
+    import torch
+    import panda_lang_manip_b200 as p
+    from panda_lang_manip_b200 import adapters
+    assert hasattr(adapters, "PandaGymVectorEnv") and hasattr(adapters, "PandaSB3VecEnv")
+    gen = torch.Generator().manual_seed(0)
+    T, M = 50, 20000
+    src = torch.randint(0, 40 * T, (M,), generator=gen)
+    start = (src // T) * T
+    gi = p.future_goal_indices(start, torch.full_like(src, T), src, her_ratio=0.8, generator=gen)
+    rel = gi >= 0
+    assert abs(rel.float().mean().item() - 0.8) < 0.02 and bool(((gi >= src) & (gi < start + T))[rel].all())
+    with __import__("pytest").raises(p.PandaB200Error):       # no device here: the relabel kernel refuses CPU tensors, there is no fallback
+        p.her_relabel("reach", "sparse", torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long))
