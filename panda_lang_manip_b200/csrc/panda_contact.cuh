@@ -136,6 +136,7 @@ template <typename T> struct CStore {   // per-thread view of the shared-memory 
 template <typename T> struct Contacts {
     CStore<T> st;
     int n, nr, cap;
+    int nB, nA;                 // contacts are collected in type order: [0, nB) object vertex on a plane, [nB, nB + nA) robot box on the table, then generic
     bool near;                  // the gripper is within 3 cm of the table or inside an object's broad-phase sphere (scheduling hint)
     bool capped;                // the last solve ran (nearly) all 50 sweeps (scheduling hint)
     PG_HD T& f(int c, int k) { return st.at(JX_SLOTS + c * REC + k); }
@@ -188,6 +189,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
             if (d < S.margin) add_contact(C, P, up, d, 3 + o, -1, S.mu[o] * S.table_mu, false, true);
         }
     }
+    C.nB = C.n;
     // 2. robot box vertices against the table top
 #pragma unroll
     for (int b = 0; b < 3; b++) {
@@ -201,6 +203,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
             if (over_table(S, P) && P.z < S.margin) add_contact(C, P, up, P.z, b, -1, S.rb_mu[b] * S.table_mu, b > 0, true);
         }
     }
+    C.nA = C.n - C.nB;
     // 3. robot box <-> object, both directions
     if (NOBJ > 0) {
 #pragma unroll
@@ -283,6 +286,8 @@ PG_HD void opspace_setup(const World<T, NOBJ>& W, const T (*Minv)[ND], const T* 
 }
 
 // per-contact decode shared by its three rows
+enum { KIND_OBJ_PLANE = 0, KIND_ROBOT_TABLE = 1, KIND_GENERIC = 2 };
+template <int K> struct KindTag { static constexpr int value = K; };
 template <typename T, int NOBJ> struct ContactCtx {
     V3<T> P, n;
     int rb;                     // robot box (-1: none)
@@ -479,17 +484,22 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                 }
                 d8[6] = dvq[7]; d8[7] = dvq[8];
             }
-            for (int c = 0; c < nc; c++) {          // contact normals
+            // Typed passes: the three kinds of contact run different row code, and a warp pays for every kind present in any of its
+            // lanes at a given contact index; looping kind by kind (collection order = kind order, so the row order is unchanged)
+            // makes lanes meet in the same code even when their counts differ.
+            const int eB = NOBJ > 0 ? C.nB : 0, eA = NOBJ > 0 ? C.nB + C.nA : nc;
+            auto normal_row = [&](int c, auto kind) {
+                constexpr int K = decltype(kind)::value;
                 ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
                 T app = C.f(c, C_APP), inv = C.f(c, C_INVD), di;
-                if (NOBJ == 0 || (X.table && X.rb >= 0)) {
+                if constexpr (K == KIND_ROBOT_TABLE) {
                     AxisRow<2, 1, T, NOBJ> row(Op, X);
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - row.jdv(d8) * inv;
                     T sum = app + di;
                     if (sum < T(0)) { di = -app; sum = T(0); }
                     C.f(c, C_APP) = sum;
                     row.apply(Op, di, d8, F8);
-                } else if (X.table) {       // object vertex on the table / ground plane
+                } else if constexpr (K == KIND_OBJ_PLANE) {       // object vertex on the table / ground plane
                     const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
                     ObjAxisRow<2, 1, T> row(X.P - ob[o].pos);
                     di = C.f(c, C_RHS) - row.jdv(dvl[o], dva[o]) * inv;
@@ -506,14 +516,15 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     contact_apply<T, NOBJ>(S, W, Op, X, X.n * di, d8, F8, dvl, dva, ob);
                 }
                 T r = div_fast(di, inv); res = fmax(res, r * r);
-            }
-            for (int c = 0; c < nc; c++) {          // implicit friction cone over the two tangent rows
+            };
+            auto friction_rows = [&](int c, auto kind) {          // implicit friction cone over the two tangent rows
+                constexpr int K = decltype(kind)::value;
                 T napp = C.f(c, C_APP);
-                if (napp <= T(0)) continue;
+                if (napp <= T(0)) return;
                 ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
                 T a1 = C.f(c, C_APP + 1), a2 = C.f(c, C_APP + 2), i1 = C.f(c, C_INVD + 1), i2 = C.f(c, C_INVD + 2);
                 T lim = C.f(c, C_MU) * napp, d1, d2;
-                if (NOBJ > 0 && X.table && X.rb < 0) {
+                if constexpr (K == KIND_OBJ_PLANE) {
                     const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
                     V3<T> r = X.P - ob[o].pos;
                     ObjAxisRow<1, -1, T> r1(r); ObjAxisRow<0, 1, T> r2(r);
@@ -524,7 +535,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
                     const T im = T(1) / S.mass[o];
                     r1.apply(W.Iinv[o], im, d1, dvl[o], dva[o]); r2.apply(W.Iinv[o], im, d2, dvl[o], dva[o]);
-                } else if (NOBJ == 0 || X.table) {
+                } else if constexpr (K == KIND_ROBOT_TABLE) {
                     AxisRow<1, -1, T, NOBJ> r1(Op, X); AxisRow<0, 1, T, NOBJ> r2(Op, X);
                     T s1 = a1 + C.f(c, C_RHS + 1) - r1.jdv(d8) * i1, s2 = a2 + C.f(c, C_RHS + 2) - r2.jdv(d8) * i2;
                     T len = sqrt(s1 * s1 + s2 * s2);
@@ -558,6 +569,16 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                 }
                 T r1 = div_fast(d1, i1), r2 = div_fast(d2, i2);
                 res = fmax(res, fmax(r1 * r1, r2 * r2));
+            };
+            {
+                int c = 0;
+                if (NOBJ > 0) for (; c < eB; c++) normal_row(c, KindTag<KIND_OBJ_PLANE>{});
+                for (; c < eA; c++) normal_row(c, KindTag<KIND_ROBOT_TABLE>{});
+                if (NOBJ > 0) for (; c < nc; c++) normal_row(c, KindTag<KIND_GENERIC>{});
+                c = 0;
+                if (NOBJ > 0) for (; c < eB; c++) friction_rows(c, KindTag<KIND_OBJ_PLANE>{});
+                for (; c < eA; c++) friction_rows(c, KindTag<KIND_ROBOT_TABLE>{});
+                if (NOBJ > 0) for (; c < nc; c++) friction_rows(c, KindTag<KIND_GENERIC>{});
             }
             if (robot_contacts) {       // fold this sweep's contact wrench back into the joint velocities: dvq += M^-1 Jx^T F8
                 T tau[ND];
