@@ -112,7 +112,7 @@ int pg_stats(pg_env* env, double out[4]);
 int pg_diverged(pg_env* env, long long* count);
 /* Scheduling introspection (host buffers): the per-env 16-bit key written by the last launch and the thread -> env map built from
  * the previous one (bits 0-4 contacts at the end of the launch, bit 5 robot contact, bit 6 solver ran all sweeps, bit 7 near a
- * contact, bit 9 full joint-limit sweep). */
+ * contact, bit 9 full joint-limit sweep, bits 10-13 generic contacts (Stack)). */
 int pg_debug_schedule(pg_env* env, unsigned short* key, int* perm);
 /* Timing introspection (handles created with PG_DEBUG_TIMING=1 in the environment): per thread slot of the last launch, the SM
  * cycles spent in the env's step code and the key it wrote; out is a host buffer of num_envs x 2 int64. */

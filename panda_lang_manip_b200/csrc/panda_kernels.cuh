@@ -207,12 +207,13 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
 // the envs are therefore bucket-sorted by the key their previous launch wrote (KEY_* in panda_env.cuh): full-limit-sweep envs,
 // envs with robot contacts, near ones, by contact count and solver cap -- heaviest first so the long blocks start early.
 // This packs envs that will execute the same contact code into the same warps.  Two passes over 1024-env chunks.
-constexpr int PERM_BUCKETS = 168, PERM_CHUNK = 1024, PERM_THREADS = 256;
+constexpr int PERM_BUCKETS = 336, PERM_CHUNK = 1024, PERM_THREADS = 384;
 __device__ __forceinline__ int perm_bucket(unsigned short key) {
     const int n = key & 0x1f, robot = (key >> 5) & 1, capped = (key >> 6) & 1, near = (key >> 7) & 1, full = (key >> 9) & 1;
     const int nq = n <= 10 ? n : 11 + min((n - 11) >> 2, 2);        // 0..13
-    const int cls = robot ? 2 : near;
-    return ((full * 3 + cls) * 14 + nq) * 2 + capped;
+    const int ngen = (key >> 10) & 15;
+    const int cls = ngen > 0 ? 3 + min((ngen - 1) >> 1, 2) : (robot ? 2 : near);     // far, near, robot on table only, 1-2 / 3-4 / 5+ generic contacts
+    return ((full * 6 + cls) * 14 + nq) * 2 + capped;
 }
 // pass 1: per-chunk bucket histogram
 static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const unsigned short* __restrict__ key, int* __restrict__ hist, int n) {
