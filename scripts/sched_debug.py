@@ -11,10 +11,11 @@ for t in range(17):
 torch.cuda.synchronize()
 key = np.zeros(n, np.uint16); perm = np.zeros(n, np.int32)
 env.lib.pg_debug_schedule(env._h, key.ctypes.data, perm.ctypes.data)
-def bucket(k):
-    nn = k & 31; robot = (k >> 5) & 1; capped = (k >> 6) & 1; near = (k >> 7) & 1; full = (k >> 9) & 1
-    nq = np.where(nn <= 10, nn, 11 + np.minimum((nn - 11) >> 2, 2)); cls = np.where(robot == 1, 2, near)
-    return ((full * 3 + cls) * 14 + nq) * 2 + capped
+def bucket(k):      # perm_bucket of csrc/panda_kernels.cuh
+    nn = k & 31; robot = (k >> 5) & 1; capped = (k >> 6) & 1; near = (k >> 7) & 1; full = (k >> 9) & 1; ngen = (k >> 10) & 15
+    nq = np.where(nn <= 10, nn, 11 + np.minimum((nn - 11) >> 2, 2))
+    cls = np.where(ngen > 0, 3 + np.minimum((ngen - 1) >> 1, 2), np.where(robot == 1, 2, near))
+    return ((full * 6 + cls) * 14 + nq) * 2 + capped
 assert np.array_equal(np.sort(perm), np.arange(n)), "perm is not a permutation"
 k = key[perm].astype(np.int64)          # key after the launch, in thread order of that launch
 b = bucket(k)
