@@ -13,7 +13,7 @@ NEUTRAL = np.array([0.0, 0.41, 0.0, -1.85, 0.0, 2.26, 0.79, 0.0, 0.0])
 TASK_ID = {"reach": 0, "push": 1, "slide": 2, "pick_and_place": 3, "stack": 4, "flip": 5}
 
 
-def _rollout(hc, task, control, seed, steps, dbl, action_fn=None):
+def _rollout(hc, task, control, seed, steps, dbl, action_fn=None, full_obs=False, obj0_xy=None):
     rng = np.random.default_rng(seed)
     oe = OracleEnv(task, control)
     goal = np.zeros(6); goal[:3] = rng.uniform([-0.15, -0.15, 0.0], [0.15, 0.15, 0.2])
@@ -22,6 +22,8 @@ def _rollout(hc, task, control, seed, steps, dbl, action_fn=None):
     if task == "flip":
         goal[:4] = [0, 0, 0, 1]
     objpos = np.array([rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), 0.03 if task == "slide" else 0.02, rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15), 0.06])
+    if obj0_xy is not None:
+        objpos[:2] = obj0_xy
     obs, ag, dg = oe.reset(goal, objpos)
     st = np.zeros(50); st[:9] = NEUTRAL
     for o in range(NOBJ[task]):
@@ -36,6 +38,8 @@ def _rollout(hc, task, control, seed, steps, dbl, action_fn=None):
         hc.hc_env_step(dbl, TASK_ID[task], 0 if control == "ee" else 1, 0, P(BASE), P(st), P(a), P(o2), P(a2), P(d2), P(r2), P(s2))
         q, qd = oe.joints()
         worst_q = max(worst_q, np.abs(st[:9] - q).max()); worst_obs = max(worst_obs, np.abs(o2[:3] - obs[:3]).max())
+        if full_obs:        # the whole observation: gripper, object poses and velocities
+            worst_obs = max(worst_obs, np.abs(o2 - obs).max())
         assert np.float32(r2[0]).tobytes() == np.float32(r).tobytes() or abs(float(r2[0]) - r) < 1e-6
     oe.close()
     return worst_q, worst_obs
@@ -51,6 +55,21 @@ def test_kernel_math_fp64_matches_oracle(hostcheck, task, control):
 def test_kernel_math_fp32_matches_oracle(hostcheck):
     wq, wo = _rollout(hostcheck, "reach", "ee", 0, 30, 0)
     assert wq < 2e-4 and wo < 2e-4
+
+
+@pytest.mark.parametrize("task", ["push", "pick_and_place", "stack"])
+def test_contact_rows_fp32_gripper_pressed_down(hostcheck, task):
+    """The contact paths of the kernel math in fp32 (typed passes, operational-space rows, generic rows on the contact-point velocity)
+    with the gripper driven into the table / the objects: full observation (object poses and velocities included) against the fp64
+    oracle over 20 free-running steps."""
+    def act(t, n):
+        a = np.zeros(n); a[2] = -1.0; a[0] = 0.3 * np.sin(0.7 * t)
+        if n > 3:
+            a[3] = -1.0 if t > 6 else 1.0
+        return a
+    for seed in range(2):
+        wq, wo = _rollout(hostcheck, task, "ee", seed, 20, 0, action_fn=act, full_obs=True, obj0_xy=(0.04 + 0.01 * seed, 0.0))   # the object sits under the gripper
+        assert wq < 5e-4 and wo < 5e-3, (task, seed, wq, wo)
 
 
 def test_joint_limit_engages_and_fast_sweep_falls_back(hostcheck):
