@@ -495,24 +495,21 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                 if constexpr (K == KIND_ROBOT_TABLE) {
                     AxisRow<2, 1, T, NOBJ> row(Op, X);
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - row.jdv(d8) * inv;
-                    T sum = app + di;
-                    if (sum < T(0)) { di = -app; sum = T(0); }
-                    C.f(c, C_APP) = sum;
+                    di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
+                    C.f(c, C_APP) = app + di;
                     row.apply(Op, di, d8, F8);
                 } else if constexpr (K == KIND_OBJ_PLANE) {       // object vertex on the table / ground plane
                     const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
                     ObjAxisRow<2, 1, T> row(X.P - ob[o].pos);
                     di = C.f(c, C_RHS) - row.jdv(dvl[o], dva[o]) * inv;
-                    T sum = app + di;
-                    if (sum < T(0)) { di = -app; sum = T(0); }
-                    C.f(c, C_APP) = sum;
+                    di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
+                    C.f(c, C_APP) = app + di;
                     row.apply(W.Iinv[o], T(1) / S.mass[o], di, dvl[o], dva[o]);
                 } else {
                     T jd = dot(X.n, contact_dv<T, NOBJ>(Op, X, d8, dvl, dva, ob));
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - jd * inv;
-                    T sum = app + di;
-                    if (sum < T(0)) { di = -app; sum = T(0); }
-                    C.f(c, C_APP) = sum;
+                    di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
+                    C.f(c, C_APP) = app + di;
                     contact_apply<T, NOBJ>(S, W, Op, X, X.n * di, d8, F8, dvl, dva, ob);
                 }
                 T r = div_fast(di, inv); res = fmax(res, r * r);

@@ -517,11 +517,11 @@ template <int D, int FIRST, typename T> PG_HD void limit_pair(const T (*Minv)[ND
     for (int h = 0; h < 2; h++) {
         const int side = h == 0 ? FIRST : 1 - FIRST;
         const T sg = side == 0 ? T(1) : T(-1);
-        T di = R.lim_rhs[2 * D + side] - sg * dv[D] * R.invD[D];
-        T app = R.lim_app[2 * D + side], sum = app + di;
-        const T sumc = fmin(fmax(sum, T(0)), T(100));
-        di = sumc != sum ? sumc - app : di;
-        R.lim_app[2 * D + side] = sumc;
+        // clamp of the accumulated impulse to [0, 100], written on the impulse change: di = clamp(di0, -app, 100 - app).  The bounds do
+        // not depend on this row's J.dv, so the chain from dv[D] to the next row's dv is FFMA -> min/max -> FFMA.
+        const T app = R.lim_app[2 * D + side];
+        const T di = fmin(fmax(R.lim_rhs[2 * D + side] - sg * dv[D] * R.invD[D], -app), T(100) - app);
+        R.lim_app[2 * D + side] = app + di;
         const T wi = sg * di;
         dv[D] += Minv[D][D] * wi;
         w += wi;
@@ -531,11 +531,9 @@ template <int D, int FIRST, typename T> PG_HD void limit_pair(const T (*Minv)[ND
     for (int k = 0; k < ND; k++) if (k != D) dv[k] += Minv[k][D] * w;
 }
 template <int D, typename T> PG_HD void motor_row(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
-    T di = R.mot_rhs[D] - dv[D] * R.invD[D];
-    T app = R.mot_app[D], sum = app + di, mx = M.max_imp[D];
-    const T sumc = fmin(fmax(sum, -mx), mx);
-    di = sumc != sum ? sumc - app : di;
-    R.mot_app[D] = sumc;
+    const T app = R.mot_app[D], mx = M.max_imp[D];
+    const T di = fmin(fmax(R.mot_rhs[D] - dv[D] * R.invD[D], -mx - app), mx - app);     // |accumulated impulse| <= max force * dt, on the change
+    R.mot_app[D] = app + di;
 #pragma unroll
     for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * di;
     T r = di * Minv[D][D]; res = fmax(res, r * r);
