@@ -496,19 +496,7 @@ template <bool PIN = false, typename T> PG_HD void joint_rows_setup(const Model<
         if (PIN) { pin(R.lim_rhs[2 * d]); pin(R.lim_rhs[2 * d + 1]); pin(R.mot_rhs[d]); }   // measured: +10 % with the watched-limit sweep, -2 % with the full one
     }
 }
-template <int D, int SIDE, typename T> PG_HD void limit_row(const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
-    const T sg = SIDE == 0 ? T(1) : T(-1);
-    T di = R.lim_rhs[2 * D + SIDE] - sg * dv[D] * R.invD[D];
-    T app = R.lim_app[2 * D + SIDE], sum = app + di;
-    const T sumc = fmin(fmax(sum, T(0)), T(100));       // impulse in [0, 100]; di is only recomputed when the clamp acts (same values, 3 instructions less)
-    di = sumc != sum ? sumc - app : di;
-    R.lim_app[2 * D + SIDE] = sumc;
-    T w = sg * di;
-#pragma unroll
-    for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * w;
-    T r = di * Minv[D][D]; res = fmax(res, r * r);
-}
-// Both limit rows of joint D, side FIRST then the other.  The same values as two limit_row calls: the joint's own velocity is updated
+// Both limit rows of joint D, side FIRST then the other.  The same values as two single rows: the joint's own velocity is updated
 // after each row (the second row reads it), the other eight joints get the two impulse changes at once -- at most one row of a
 // pair carries impulse, the other's change is exactly zero, so the sum is that one change.  Saves 8 FMAs per joint and sweep.
 template <int D, int FIRST, typename T> PG_HD void limit_pair(const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
