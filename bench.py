@@ -211,27 +211,32 @@ def run_gpu(args):
     # configs[3]'s per-GPU batch, timed the same way (informational: the headline `value` is the workload named in `config`)
     also = None
     if args.task == "reach" and args.control == "joints" and not args.no_her:
-        try:
-            n2 = 32768
+        n2, k2, sec2, err2 = 32768, 40, -1.0, None
+        try:                          # rank-local work only inside the try: a failure on one rank must not leave the others in a collective
             env2 = p.PandaVecEnv("pick_and_place", n2, reward_type=args.reward, control_type="ee", device=local, seed=args.seed, env_id_offset=rank * n2, auto_reset=True)
             act2 = torch.rand((ncyc, n2, 4), device=dev, generator=gen) * 2 - 1
             for w in range(10):
                 env2.step(act2[w % ncyc])
-            barrier()
-            k2 = 40
+            torch.cuda.synchronize(dev)
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k2)]
             for k, (a, b) in enumerate(ev):
                 flush.zero_()
                 a.record(); env2.step(act2[k % ncyc]); b.record()
-            barrier()
-            t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / 1e3], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-            also = {"workload": workload_name("pick_and_place", "ee", args.reward, n2), "value": world * n2 * k2 / float(t2.item()), "unit": "env-steps/s",
-                    "ms_per_step": 1e3 * float(t2.item()) / k2, "steps": k2, "warmup": 10, "envs_per_gpu": n2}
+            torch.cuda.synchronize(dev)
+            sec2 = sum(a.elapsed_time(b) for a, b in ev) / 1e3
             env2.close(); del act2
-        except Exception as exc:      # never let the informational leg break the line
-            also = {"error": repr(exc)}
+        except Exception as exc:
+            err2 = repr(exc)
+        t2 = torch.tensor([sec2, 1.0 if err2 is None else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t2.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)       # slowest rank
+            tmin = t2.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)       # did every rank succeed?
+            t2 = torch.stack([tmax[0], tmin[1]])
+        if float(t2[1].item()) == 1.0 and float(t2[0].item()) > 0:
+            also = {"workload": workload_name("pick_and_place", "ee", args.reward, n2), "value": world * n2 * k2 / float(t2[0].item()), "unit": "env-steps/s",
+                    "ms_per_step": 1e3 * float(t2[0].item()) / k2, "steps": k2, "warmup": 10, "envs_per_gpu": n2}
+        else:
+            also = {"error": err2 or "failed on another rank"}
 
     # HER relabelling kernel (the one genuinely HBM-bound kernel of the path): compute_reward on M transitions
     her = None
