@@ -17,7 +17,8 @@
 extern "C" {
 #endif
 
-enum { PG_TASK_REACH = 0, PG_TASK_PUSH = 1, PG_TASK_SLIDE = 2, PG_TASK_PICK_AND_PLACE = 3, PG_TASK_STACK = 4, PG_TASK_FLIP = 5 };
+enum { PG_TASK_REACH = 0, PG_TASK_PUSH = 1, PG_TASK_SLIDE = 2, PG_TASK_PICK_AND_PLACE = 3, PG_TASK_STACK = 4, PG_TASK_FLIP = 5,
+       PG_TASK_BARE = 6 /* handles made by pg_create_bare: the sim facade without a task */ };
 enum { PG_CTRL_EE = 0, PG_CTRL_JOINTS = 1 };          /* panda_gym/envs/robots/panda.py:21-33 control_type */
 enum { PG_REWARD_SPARSE = 0, PG_REWARD_DENSE = 1 };   /* panda_gym/envs/tasks/reach.py:60-65 reward_type */
 enum { PG_F32 = 0, PG_F64 = 1 };
@@ -30,6 +31,23 @@ typedef struct pg_env pg_env;
  * device RNG by GLOBAL environment index, so a sharded run reproduces the unsharded one.  All envs start reset. */
 int pg_create(int task, int control_type, int reward_type, int num_envs, int device, unsigned long long seed,
               long long env_id_offset, int precision, pg_env** out);
+/* The reference's sim facade used WITHOUT a task (panda_gym/pybullet.py:16-68: PyBullet() + loadURDF :510-529 + create_box / create_cylinder
+ * :531-719 + create_table / create_plane :726-771), as its own tests do (test/pybullet_test.py:56-65,110-265): num_envs identical
+ * worlds holding the Panda at robot_base (NULL: no robot), n_bodies <= 2 free bodies -- HOST rows
+ * [shape (0 box, 1 z-cylinder), hx, hy, hz (half extents; cylinder: r, r, h/2), mass, lateral friction, pos3, quat4 (x,y,z,w)] --,
+ * an optional table top at z = 0 over table_rect = {x0, x1, y0, y1} (HOST, NULL: none) and an optional ground plane at *ground_z
+ * (HOST, NULL: none).  Joints start at 0 with the velocity motors loadURDF leaves (target 0, max impulse 1 per sub-step).
+ * Such a handle is advanced with pg_sim_step and driven with pg_set_motors; pg_get_state / pg_set_state / pg_get_link_state /
+ * pg_inverse_kinematics_link / snapshots work as on task handles (state rows without a goal). */
+int pg_create_bare(int num_envs, int device, int precision, const double* robot_base, int n_bodies, const double* bodies,
+                   const double* table_rect, const double* ground_z, pg_env** out);
+/* PyBullet.control_joints -> setJointMotorControlArray (pybullet.py:462-477), per world: DEVICE rows [N, 9, 5] =
+ * {position gain, velocity gain, target angle, target velocity, max force} for joints 0-6, 9, 10 (POSITION_CONTROL as the
+ * reference issues it: 0.1, 1.0, target, 0, force).  mask (DEVICE, NULL = all) selects the worlds that are written. */
+int pg_set_motors(pg_env* env, const double* motors, const unsigned char* mask, void* stream);
+int pg_get_motors(pg_env* env, double* motors, void* stream);
+/* PyBullet.step (pybullet.py:52-55): n_substeps x stepSimulation of a bare world with its current motors. */
+int pg_sim_step(pg_env* env, int n_substeps, void* stream);
 int pg_destroy(pg_env* env);                                            /* RobotTaskEnv.close, core.py:291-292 */
 /* observation / goal / action widths and the TimeLimit length (panda_gym/__init__.py:18,46) */
 int pg_dims(const pg_env* env, int* obs_dim, int* goal_dim, int* action_dim, int* max_episode_steps, int* state_dim);
@@ -40,6 +58,21 @@ int pg_dims(const pg_env* env, int* obs_dim, int* goal_dim, int* action_dim, int
  * Writes obs/ag/dg rows of the reset envs only (any of them may be NULL). */
 int pg_reset(pg_env* env, const unsigned char* mask, const double* goal_override, const double* object_override,
              float* obs, float* achieved_goal, float* desired_goal, void* stream);
+/* RobotTaskEnv.reset(seed=k) batched (core.py:240-244: the task RNG is re-created from the seed): seeds [N] uint64 (DEVICE; NULL =
+ * pg_reset) key each reset env's draws by ITS seed alone, so equal seeds give equal goals / object placements in any env of any
+ * handle (reference test/seed_test.py).  The draws come from the device's Philox stream, not numpy's PCG64 -- the single-env facade
+ * reproduces the reference's seeded values bit-for-bit on the host and injects them through the overrides. */
+int pg_reset_seeded(pg_env* env, const unsigned char* mask, const unsigned long long* seeds, const double* goal_override,
+                    const double* object_override, float* obs, float* achieved_goal, float* desired_goal, void* stream);
+/* The task constructors' keyword arguments (tasks/reach.py:15-23 distance_threshold, goal_range; push.py:12-25; slide.py:12-27;
+ * pick_and_place.py:13-29; stack.py:11-25; flip.py:13-24) as kernel parameters: the success / sparse-reward threshold used inside
+ * pg_step, the goal noise box [low, high] (3 doubles each, HOST; what the reference builds from goal_range / goal_xy_range /
+ * goal_z_range / goal_x_offset) and the object xy noise box (2 doubles each; obj_xy_range).  NULL keeps a range.  Takes effect
+ * from the next reset / step. */
+int pg_set_task_params(pg_env* env, double distance_threshold, const double* goal_range_low, const double* goal_range_high,
+                       const double* obj_range_low, const double* obj_range_high);
+/* PyBullet(n_substeps=...) (pybullet.py:26,39,52-55): stepSimulation calls per env step (default 20). */
+int pg_set_substeps(pg_env* env, int n_substeps);
 
 /* RobotTaskEnv.step (core.py:280-289) for every env: Panda.set_action (panda.py:52-70), 20 x stepSimulation
  * (pybullet.py:52-55), _get_obs (core.py:229-238), is_success, compute_reward; truncated = TimeLimit.
@@ -75,6 +108,12 @@ int pg_compute_reward(int task, int reward_type, const void* achieved_goal, cons
                       long long m, int dtype, void* stream);
 int pg_is_success(int task, const void* achieved_goal, const void* desired_goal, unsigned char* success, long long m,
                   int dtype, void* stream);
+/* The same with the task's distance_threshold as an argument (the two calls above use the reference's defaults 0.05 / 0.1 / 0.2);
+ * the threshold is compared in the dtype of the distance, as numpy does with a Python-float threshold. */
+int pg_compute_reward_t(int task, int reward_type, double threshold, const void* achieved_goal, const void* desired_goal,
+                        float* reward, long long m, int dtype, void* stream);
+int pg_is_success_t(int task, double threshold, const void* achieved_goal, const void* desired_goal, unsigned char* success,
+                    long long m, int dtype, void* stream);
 /* HER relabelling fused with compute_reward (replaces the gather + env.compute_reward round trip of stable-baselines3's
  * HerReplayBuffer that reference examples/train_push.py:1-12 sets up; rewards as tasks/<task>.py compute_reward).  next_achieved_goal and
  * desired_goal are the replay buffer's [R, G] goal arrays (device); for each of the M sampled transitions j: the new goal is
@@ -83,16 +122,30 @@ int pg_is_success(int task, const void* achieved_goal, const void* desired_goal,
 int pg_her_relabel(int task, int reward_type, const void* next_achieved_goal, const void* desired_goal, const long long* src,
                    const long long* goal_src, void* desired_goal_out, void* achieved_goal_out, float* reward, long long m, int dtype,
                    void* stream);
+int pg_her_relabel_t(int task, int reward_type, double threshold, const void* next_achieved_goal, const void* desired_goal,
+                     const long long* src, const long long* goal_src, void* desired_goal_out, void* achieved_goal_out, float* reward,
+                     long long m, int dtype, void* stream);
+/* Task.compute_reward / is_success on HOST arrays (what RobotTaskEnv.compute_reward, core.py:226, is called with by a CPU learner). */
 int pg_compute_reward_host(int task, int reward_type, const void* achieved_goal, const void* desired_goal, float* reward,
                            long long m, int dtype, int device);
+int pg_compute_reward_host_t(int task, int reward_type, double threshold, const void* achieved_goal, const void* desired_goal,
+                             float* reward, long long m, int dtype, int device);
+int pg_is_success_host_t(int task, double threshold, const void* achieved_goal, const void* desired_goal, unsigned char* success,
+                         long long m, int dtype, int device);
 int pg_is_success_host(int task, const void* achieved_goal, const void* desired_goal, unsigned char* success, long long m,
                        int dtype, int device);
+/* The two _host calls above stage through per-device buffers that only grow: number of (re)allocations so far (diagnostic). */
+long long pg_host_stage_allocations(void);
 
 /* RobotTaskEnv.save_state / restore_state / remove_state (core.py:252-278; pybullet.py:61-68,266-280): bit-exact device
  * snapshot of the whole batch (state, goals, episode counters). */
-int pg_save_state(pg_env* env, int* state_id);
+int pg_save_state(pg_env* env, int* state_id);         /* blocking, on the legacy default stream */
 int pg_restore_state(pg_env* env, int state_id);
 int pg_remove_state(pg_env* env, int state_id);
+/* Stream-ordered forms: one device-to-device copy enqueued on `stream`, no synchronisation; a removed snapshot's buffer is reused
+ * by the next save, so a save / restore / remove loop allocates nothing after its first round and can be captured in a CUDA graph. */
+int pg_save_state_async(pg_env* env, int* state_id, void* stream);
+int pg_restore_state_async(pg_env* env, int state_id, void* stream);
 
 /* Raw state exchange for the facade getters/setters (pybullet.py:284-460) and the parity tests: float64 rows
  * [q(9) qd(9) | per object: pos(3) quat(4) lin(3) ang(3) | goal(G) | episode step], state_dim wide. */
@@ -101,6 +154,13 @@ int pg_set_state(pg_env* env, const double* state, const unsigned char* mask, vo
 /* calculateInverseKinematics on link 11 from the current joint state (pybullet.py:479-497): target [N,3] + quat [N,4]
  * float64 -> joint angles [N,7] float64. */
 int pg_inverse_kinematics(pg_env* env, const double* position, const double* orientation, double* joint_angles, void* stream);
+/* The same call for any link 0..11 (PyBullet.inverse_kinematics(body, link, ...), pybullet.py:479-497; the reference's known-answer
+ * test uses link 6, test/pybullet_test.py:254-266): all nine joint values per row, [N,9] float64. */
+int pg_inverse_kinematics_link(pg_env* env, int link, const double* position, const double* orientation, double* joint_angles, void* stream);
+/* getLinkState of any link 0..11 (PyBullet.get_link_position / _orientation / _velocity / _angular_velocity, pybullet.py:351-400):
+ * rows [pos3 quat4 (x,y,z,w) lin3 ang3] float64 of the link's CoM frame; like pybullet without computeForwardKinematics, the pose
+ * comes from the link-transform cache (one sub-step stale) and the velocity is rotated by the cached basis. */
+int pg_get_link_state(pg_env* env, int link, double* out, void* stream);
 
 /* End-effector (link 11) pose from the current joint state, rows [x y z qx qy qz qw] float64 (the fork's get_ee_position /
  * get_ee_orientation, panda_gym/envs/robots/panda_cartesian.py:218-225). */

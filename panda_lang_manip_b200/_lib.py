@@ -12,6 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("PANDA_B200_LIB", os.path.join(CSRC, "libpanda_b200.so"))   # override: A/B builds of the same ABI
 
 TASKS = {"reach": 0, "push": 1, "slide": 2, "pick_and_place": 3, "stack": 4, "flip": 5}
+TASK_BARE = 6
 CONTROL = {"ee": 0, "joints": 1}
 REWARD = {"sparse": 0, "dense": 1}
 PRECISION = {"f32": 0, "f64": 1}
@@ -19,7 +20,8 @@ PRECISION = {"f32": 0, "f64": 1}
 SYMBOLS = [
     "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_host_pin", "pg_host_unpin", "pg_compute_reward", "pg_is_success",
     "pg_compute_reward_host", "pg_is_success_host", "pg_her_relabel", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
-    "pg_inverse_kinematics", "pg_get_ee_pose", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
+    "pg_inverse_kinematics", "pg_get_ee_pose", "pg_create_bare", "pg_set_motors", "pg_get_motors", "pg_sim_step", "pg_inverse_kinematics_link", "pg_get_link_state",
+    "pg_save_state_async", "pg_restore_state_async", "pg_host_stage_allocations", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
 _lib = None
@@ -66,6 +68,15 @@ def load() -> ctypes.CDLL:
     lib.pg_set_state.argtypes = [vp, vp, vp, vp]
     lib.pg_inverse_kinematics.argtypes = [vp, vp, vp, vp, vp]
     lib.pg_get_ee_pose.argtypes = [vp, vp, vp]
+    lib.pg_create_bare.argtypes = [c_int, c_int, c_int, vp, c_int, vp, vp, vp, ctypes.POINTER(vp)]
+    lib.pg_set_motors.argtypes = [vp, vp, vp, vp]
+    lib.pg_get_motors.argtypes = [vp, vp, vp]
+    lib.pg_sim_step.argtypes = [vp, c_int, vp]
+    lib.pg_inverse_kinematics_link.argtypes = [vp, c_int, vp, vp, vp, vp]
+    lib.pg_get_link_state.argtypes = [vp, c_int, vp, vp]
+    lib.pg_save_state_async.argtypes = [vp, pi, vp]
+    lib.pg_restore_state_async.argtypes = [vp, c_int, vp]
+    lib.pg_host_stage_allocations.restype = c_ll
     lib.pg_debug_schedule.argtypes = [vp, vp, vp]
     lib.pg_debug_timing.argtypes = [vp, vp]
     lib.pg_diverged.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]

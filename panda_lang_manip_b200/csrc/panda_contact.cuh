@@ -7,8 +7,9 @@
 // Contact model (defined by oracle/panda_oracle.c, "contact model"): vertices of one body against the signed-distance
 // field of the other (table plane, box, z-cylinder), speculative rows inside a 4 mm margin, two friction directions with an
 // implicit cone, soft finger contacts, sequential impulses interleaved with the joint-limit and motor rows.
-// Rows are kept in per-thread local memory (interleaved, so a warp's accesses coalesce); the robot part of a row is a
-// 9-vector pair (J, M^-1 J^T), the free-body part is recomputed from the contact geometry each sweep.
+// Contact records (geometry + 3 x (1/D, rhs, impulse)) and the operational-space Jacobian live in shared memory, word-interleaved
+// by thread; the robot part of a row is a wrench in the gripper's 8-dimensional operational space, the free-body part is
+// recomputed from the contact geometry each sweep (see "contact storage" below).
 #pragma once
 #include "panda_dyn.cuh"
 
@@ -609,8 +610,9 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
     return live;
 }
 
-template <typename T, int NOBJ, bool WATCH_LIMITS>
-PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep, bool& limits_active) {
+template <typename T, int NOBJ, bool WATCH_LIMITS, bool GENERIC_MOTORS = false>
+PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep, bool& limits_active,
+                       const T* mot = nullptr) {
     T sn[7], cs[7], Minv[ND][ND], qdd[ND];
     robot_dynamics(M, q, qd, sn, cs, Minv, qdd);
 #pragma unroll
@@ -643,7 +645,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
         W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
     }
     JointRows<T> R;
-    joint_rows_setup<WATCH_LIMITS>(M, q, qd, target, Minv, R);
+    joint_rows_setup<WATCH_LIMITS, GENERIC_MOTORS>(M, q, qd, target, Minv, R, mot);
     collect_contacts<T, NOBJ>(S, W, ob, C);
     OpSpace<T> Op;
     const bool robot_contacts = C.nr > 0;

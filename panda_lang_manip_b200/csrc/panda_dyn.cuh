@@ -34,6 +34,7 @@ template <typename T> struct Model {
     T m[9], h[9][3], Io[9][6];  // per dynamic body: mass, first moment, inertia about the body-frame origin (xx,xy,xz,yy,yz,zz)
     T dm[NPART], dc[NPART][3], dI[NPART][3];  // per damped part: mass, CoM in body coords, principal inertia (part axes)
     T lo[9], hi[9], max_imp[9]; // joint limits, motor impulse limit per sub-step (force * dt)
+    T z7;                       // hand frame height above the link-6 origin (panda_joint8: 0.107)
     T hz;                       // finger joint frame height above the link-6 origin (0.107 + 0.0584)
     T eez;                      // grasp-target frame height above the link-6 origin (0.107 + 0.105)
     T fa[2];                    // finger slide direction sign in hand axes (+1, -1)
@@ -458,6 +459,117 @@ template <typename T> PG_HD void ik_ee(const Model<T>& M, const T* q0, V3<T> tar
     for (int i = 0; i < 7; i++) qout[i] = q[i];
 }
 
+// ---------------------------------------------------------------------------------------------- any-link kinematics
+// What getLinkState / calculateInverseKinematics see for an arbitrary link index 0..11 (reference panda_gym/pybullet.py:351-400,
+// :479-497; link table: SURVEY App. C).  Links 0..6 are the arm links, 7 = panda_link8 (fixed, +0.107 z), 8 = hand (yaw -45 deg),
+// 9 / 10 = fingers (prismatic along +-y of the hand), 11 = grasp target (+0.105 z of the hand).
+template <typename T> PG_HD Frame<T> link_frame_from(const Model<T>& M, const Frame<T>* F, const T* q, int link) {
+    if (link <= 6) return F[link];
+    Frame<T> L = F[6];
+    L.p = F[6].p + F[6].Z * M.z7;
+    if (link == 7) return L;
+    const T k = Consts<T>::k45;
+    L.X = (F[6].X - F[6].Y) * k; L.Y = (F[6].X + F[6].Y) * k;
+    if (link == 9) L.p = F[6].p + F[6].Z * M.hz + L.Y * q[7];
+    else if (link == 10) L.p = F[6].p + F[6].Z * M.hz - L.Y * q[8];
+    else if (link == 11) L.p = F[6].p + F[6].Z * M.eez;
+    return L;
+}
+// centre of mass of a link in its own frame (getLinkState[0] is the CoM frame; massless links: the frame origin)
+template <typename T> PG_HD V3<T> link_com(const Model<T>& M, int link) {
+    if (link <= 6) return ld3(M.dc[link]);
+    if (link == 8) return mk<T>(M.dc[7][0], M.dc[7][1], M.dc[7][2] - M.z7);
+    if (link == 9) return ld3(M.dc[8]);
+    if (link == 10) return ld3(M.dc[9]);
+    return mk<T>(T(0), T(0), T(0));
+}
+// spatial velocity of arm link `link` (<= 6) in its own coordinates at its frame origin
+template <typename T> PG_HD SV<T> arm_link_velocity(const Model<T>& M, const T* q, const T* qd, int link) {
+    SV<T> v; v.a = mk<T>(0, 0, 0); v.l = mk<T>(0, 0, 0);
+    v = vel_next<0>(M, v, q[0], qd[0]); if (link == 0) return v;
+    v = vel_next<1>(M, v, q[1], qd[1]); if (link == 1) return v;
+    v = vel_next<2>(M, v, q[2], qd[2]); if (link == 2) return v;
+    v = vel_next<3>(M, v, q[3], qd[3]); if (link == 3) return v;
+    v = vel_next<4>(M, v, q[4], qd[4]); if (link == 4) return v;
+    v = vel_next<5>(M, v, q[5], qd[5]); if (link == 5) return v;
+    return vel_next<6>(M, v, q[6], qd[6]);
+}
+// getLinkState(link, computeLinkVelocity=1) without computeForwardKinematics: pose of the CoM frame from the
+// cached transforms FK(qc); velocity = link-local velocity from the fresh (q, qd), rotated to the world by the cached basis.
+template <typename T> PG_HD void link_state(const Model<T>& M, int link, const T* q, const T* qd, const T* qc, V3<T>& pos, T* quat, V3<T>& lin, V3<T>& ang) {
+    Frame<T> F[7]; fk_arm(M, qc, F);
+    Frame<T> L = link_frame_from(M, F, qc, link);
+    V3<T> c = link_com(M, link);
+    pos = L.p + L.X * c.x + L.Y * c.y + L.Z * c.z;
+    rot_to_quat(L, quat);
+    if (link <= 6) {
+        SV<T> v = arm_link_velocity(M, q, qd, link);
+        V3<T> vc = v.l + cross(v.a, c);
+        lin = L.X * vc.x + L.Y * vc.y + L.Z * vc.z; ang = L.X * v.a.x + L.Y * v.a.y + L.Z * v.a.z;
+    } else {
+        // links riding on link 6: velocity in hand axes at the link's CoM (fresh q for the finger offsets), rotated by the cached hand basis
+        SV<T> v6 = arm_link_velocity(M, q, qd, 6);
+        V3<T> w = l6_to_hand(v6.a);
+        T oz = link == 7 || link == 8 ? M.z7 : (link == 11 ? M.eez : M.hz);
+        T oy = link == 9 ? q[7] : (link == 10 ? -q[8] : T(0));
+        V3<T> r = mk<T>(c.x, oy + c.y, oz + c.z);                      // CoM relative to the link-6 origin, hand axes
+        V3<T> vl = l6_to_hand(v6.l) + cross(w, r);
+        if (link == 9) vl.y += qd[7]; else if (link == 10) vl.y -= qd[8];
+        Frame<T> H = link_frame_from(M, F, qc, 8);
+        lin = H.X * vl.x + H.Y * vl.y + H.Z * vl.z; ang = H.X * w.x + H.Y * w.y + H.Z * w.z;
+    }
+}
+// calculateInverseKinematics for an arbitrary link (the facade's PyBullet.inverse_kinematics; ik_ee below is the env path's fixed
+// link-11 instance): the same 20 DLS iterations on the URDF frame origin of `link`, all 9 dofs (finger columns are the slide
+// directions for links 9 / 10, zero otherwise), no joint-limit clamping.  tq = unit target quaternion (x,y,z,w).
+template <typename T> PG_HD void ik_link(const Model<T>& M, int link, const T* q0, V3<T> target, const T* tq, T* qout) {
+    T q[ND];
+#pragma unroll
+    for (int i = 0; i < ND; i++) q[i] = q0[i];
+    T diff = T(1e30);
+    for (int it = 0; it < 20 && diff > T(1e-4); it++) {
+        Frame<T> F[7]; fk_arm(M, q, F);
+        Frame<T> E = link_frame_from(M, F, q, link);
+        V3<T> ep = target - E.p;
+        diff = norm(ep);
+        T qr[4]; rot_to_quat(E, qr);
+        T ax = -qr[0], ay = -qr[1], az = -qr[2], aw = qr[3];
+        T dx = tq[3] * ax + tq[0] * aw + tq[1] * az - tq[2] * ay;
+        T dy = tq[3] * ay - tq[0] * az + tq[1] * aw + tq[2] * ax;
+        T dz = tq[3] * az + tq[0] * ay - tq[1] * ax + tq[2] * aw;
+        T dw = tq[3] * aw - tq[0] * ax - tq[1] * ay - tq[2] * az;
+        T vn = sqrt(dx * dx + dy * dy + dz * dz);
+        T ang = 2 * atan2(vn, dw);
+        if (ang > Consts<T>::pi) ang -= 2 * Consts<T>::pi;
+        T sc = vn > T(1e-12) ? ang / vn : T(0);
+        T e[6] = {ep.x, ep.y, ep.z, dx * sc, dy * sc, dz * sc};
+        T J[6][ND];
+        for (int j = 0; j < ND; j++) {
+            V3<T> l = mk<T>(T(0), T(0), T(0)), a = l;
+            if (j < 7) { if (j <= link) { a = F[j].Z; l = cross(a, E.p - F[j].p); } }
+            else if (link == j + 2) l = E.Y * M.fa[j - 7];
+            J[0][j] = l.x; J[1][j] = l.y; J[2][j] = l.z; J[3][j] = a.x; J[4][j] = a.y; J[5][j] = a.z;
+        }
+        T A[6][6], y[6];
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b <= a; b++) { T t = (a == b) ? T(0.5) : T(0); for (int j = 0; j < ND; j++) t += J[a][j] * J[b][j]; A[a][b] = t; }
+        for (int j = 0; j < 6; j++) {       // Cholesky (reciprocal diagonal), forward / backward substitution
+            T d = A[j][j]; for (int kk = 0; kk < j; kk++) d -= A[j][kk] * A[j][kk];
+            T inv = T(1) / sqrt(d); A[j][j] = inv;
+            for (int i = j + 1; i < 6; i++) { T t = A[i][j]; for (int kk = 0; kk < j; kk++) t -= A[i][kk] * A[j][kk]; A[i][j] = t * inv; }
+        }
+        for (int i = 0; i < 6; i++) { T t = e[i]; for (int kk = 0; kk < i; kk++) t -= A[i][kk] * y[kk]; y[i] = t * A[i][i]; }
+        for (int i = 5; i >= 0; i--) { T t = y[i]; for (int kk = i + 1; kk < 6; kk++) t -= A[kk][i] * y[kk]; y[i] = t * A[i][i]; }
+        T dth[ND], mx = T(0);
+        for (int j = 0; j < ND; j++) { T t = T(0); for (int a = 0; a < 6; a++) t += J[a][j] * y[a]; dth[j] = t; mx = fmax(mx, fabs(t)); }
+        const T lim = Consts<T>::pi / 4;
+        T scl = mx > lim ? lim / mx : T(1);
+        for (int j = 0; j < ND; j++) q[j] += dth[j] * scl;
+    }
+#pragma unroll
+    for (int i = 0; i < ND; i++) qout[i] = q[i];
+}
+
 // ---------------------------------------------------------------------------------------------- joint-space constraint rows
 // btMultiBodyJointLimitConstraint (2 rows per joint, link order) then btMultiBodyJointMotor.  A joint-space
 // row's Jacobian is +-e_d, so its impulse response is a column of Minv.
@@ -478,7 +590,9 @@ PG_HD void pin(double& x) {
     asm volatile("" : "+d"(x));
 #endif
 }
-template <bool PIN = false, typename T> PG_HD void joint_rows_setup(const Model<T>& M, const T* q, const T* qd, const T* target, const T (*Minv)[ND], JointRows<T>& R) {
+// `mot` (generic motors, the bare world's setJointMotorControlArray state): [0..8] position gain kp, [9..17] velocity gain kd,
+// [18..26] target velocity; NULL = the env path's POSITION_CONTROL defaults (kp 0.1, kd 1, target velocity 0).
+template <bool PIN = false, bool GENERIC = false, typename T> PG_HD void joint_rows_setup(const Model<T>& M, const T* q, const T* qd, const T* target, const T (*Minv)[ND], JointRows<T>& R, const T* mot = nullptr) {
     const T inv_dt = Consts<T>::inv_dt;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
@@ -492,6 +606,7 @@ template <bool PIN = false, typename T> PG_HD void joint_rows_setup(const Model<
         R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0);
         // POSITION_CONTROL, kp = 0.1, kd = 1, target velocity 0: desired velocity 0.1 (q* - q)/dt
         T vt = T(0.1) * (target[d] - q[d]) * inv_dt;
+        if (GENERIC) vt = mot[d] * (target[d] - q[d]) * inv_dt + qd[d] + mot[9 + d] * (mot[18 + d] - qd[d]);   // btMultiBodyJointMotor: kp (q* - q)/dt + v + kd (v* - v)
         R.mot_rhs[d] = (vt - qd[d]) * invD; R.mot_app[d] = T(0);
         if (PIN) { pin(R.lim_rhs[2 * d]); pin(R.lim_rhs[2 * d + 1]); pin(R.mot_rhs[d]); }   // measured: +10 % with the watched-limit sweep, -2 % with the full one
     }

@@ -20,6 +20,24 @@ PG_HD constexpr int task_obs_dim(int task) { return (task_block_gripper(task) ? 
 PG_HD constexpr int task_act_dim(int task, int ctrl) { return (ctrl == CTRL_EE ? 3 : 7) + (task_block_gripper(task) ? 0 : 1); }
 PG_HD constexpr int task_max_steps(int task) { return task == TASK_STACK ? 100 : 50; }   // panda_gym/__init__.py:18,46
 
+// What the reference's task constructors take as keyword arguments (tasks/reach.py:15-23 distance_threshold, goal_range; push.py:12-25,
+// slide.py:12-27, pick_and_place.py:13-29, stack.py:11-25, flip.py:13-24: goal_xy_range, goal_z_range, goal_x_offset, obj_xy_range) and
+// PyBullet(n_substeps) (pybullet.py:26), as kernel parameters.  Ranges are the noise boxes added to the task's base goal / object height.
+struct TaskParams {
+    double goal_lo[3], goal_hi[3];  // goal noise box
+    double obj_lo[2], obj_hi[2];    // object xy noise box
+    double thr64; float thr32;      // distance_threshold (compared in the dtype of the distance, as numpy does)
+    int nsub;                       // stepSimulation calls per env step
+};
+inline TaskParams make_task_params(int task) {
+    TaskParams P;
+    const double z_hi = task == 0 ? 0.3 : (task == 3 ? 0.2 : 0.0), x_off = task == 2 ? 0.4 : 0.0;
+    P.goal_lo[0] = -0.15 + x_off; P.goal_hi[0] = 0.15 + x_off; P.goal_lo[1] = -0.15; P.goal_hi[1] = 0.15; P.goal_lo[2] = 0.0; P.goal_hi[2] = z_hi;
+    P.obj_lo[0] = P.obj_lo[1] = -0.15; P.obj_hi[0] = P.obj_hi[1] = 0.15;
+    P.thr64 = task == 4 ? 0.1 : (task == 5 ? 0.2 : 0.05); P.thr32 = (float)P.thr64; P.nsub = 20;
+    return P;
+}
+
 // float32 arithmetic exactly as numpy evaluates it: no fused multiply-add
 #ifdef __CUDA_ARCH__
 PG_HD float f_sub(float a, float b) { return __fsub_rn(a, b); }
@@ -165,7 +183,8 @@ enum { KEY_ROBOT = 0x20, KEY_CAPPED = 0x40, KEY_NEAR = 0x80, KEY_FULL = 0x200 };
 // reward and success are produced by the segment that ends the step (s1 == 20).
 template <typename T, int TASK, int CTRL>
 PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action, const float* target_quat,
-                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& sched_key, T* target, int s0 = 0, int s1 = 20) {
+                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& sched_key, T* target, int s0 = 0, int s1 = 20,
+                    int nsub = 20, float thr = -1.0f) {
     constexpr int NOBJ = task_nobj(TASK);
     T qc[ND];
     if (s0 == 0) env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
@@ -174,7 +193,7 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
     bool full_sweep = (sched_key & KEY_FULL) != 0, limits_active = false;
     int nsub_contact = 0; bool near = false;
     for (int s = s0; s < s1; s++) {
-        if (s == 19) {
+        if (s == nsub - 1) {
 #pragma unroll
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
@@ -187,9 +206,10 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
     // scheduling key for the next launch (see perm_bucket): the contact picture of this launch's last sub-step
     const int ngen = C.n - C.nB - C.nA;                     // generic contacts (robot box <-> object, object <-> object): the most expensive rows
     sched_key = (C.n < 31 ? C.n : 31) | (NOBJ == 2 ? (ngen < 15 ? ngen : 15) << 10 : 0) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (limits_active ? KEY_FULL : 0);
-    if (s1 < 20) return;
+    if (s1 < nsub) return;
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
-    float d = goal_distance(TASK, ag, dg), thr = threshold_f32(TASK);
+    if (thr < 0.0f) thr = threshold_f32(TASK);
+    float d = goal_distance(TASK, ag, dg);
     success = d < thr;
     reward = reward_from_distance(reward_type, d, thr);
 }

@@ -20,7 +20,8 @@ template <typename T> struct EnvDev {
     T* qd;                       // [9][n]
     T* obj;                      // [nobj][13][n]  pos3 quat4 lin3 ang3
     T* goal;                     // [6][n]
-    T* target;                   // [9][n] motor targets of the step in flight (only live between the segments of a cut step)
+    T* target;                   // [9][n] motor targets of the step in flight (only live between the segments of a cut step); bare worlds: the motors' target angles
+    T* motor;                    // bare worlds only: [4][9][n] position gain, velocity gain, target velocity, max impulse per sub-step (setJointMotorControlArray state)
     int* steps;                  // [n] steps since reset (TimeLimit)
     unsigned* episode;           // [n] episodes started (RNG counter)
     float* ret;                  // [n] running episode return
@@ -32,15 +33,17 @@ template <typename T> struct EnvDev {
     int* hist;                   // [ceil(n/1024)][24] scratch of the bucket sort
     Model<T> M;
     Scene<T> S;
+    TaskParams P;
 };
 struct StepIO {
     const float* target_quat;    // [n,4] (x,y,z,w) EE target orientation for ee control, or NULL = (1,0,0,0)
     const float* actions; float* obs; float* ag; float* dg; float* reward; unsigned char* terminated; unsigned char* truncated;
     int auto_reset;
-    int s0, s1;                  // sub-step range of this launch: [0,20) = a whole step
+    int s0, s1;                  // sub-step range of this launch: [0, nsub) = a whole step
 };
 struct ResetIO {
     const unsigned char* mask; const double* goal_override; const double* object_override; float* obs; float* ag; float* dg;
+    const unsigned long long* seeds;   // [n] per-env seeds (RobotTaskEnv.reset(seed=k), core.py:240-244: equal seeds give equal draws), or NULL = the handle's stream
 };
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
@@ -66,16 +69,16 @@ struct Philox {
 };
 
 // ---------------------------------------------------------------------------------------------- I/O tiles
-// rows [row0, row0 + BLOCK) of a row-major [n, W] array <-> per-thread registers, through shared memory
-template <int W, typename E> __device__ __forceinline__ void tile_load(E* s, const E* g, long long row0, int n, E* reg) {
+// rows [row0, row0 + BS) of a row-major [n, W] array <-> per-thread registers, through shared memory
+template <int W, typename E, int BS = BLOCK> __device__ __forceinline__ void tile_load(E* s, const E* g, long long row0, int n, E* reg) {
     const long long base = row0 * W;
-    const int cnt = (int)min((long long)BLOCK, (long long)n - row0) * W;
+    const int cnt = (int)min((long long)BS, (long long)n - row0) * W;
     if (sizeof(E) == 4 && ((uintptr_t)(g + base) & 15) == 0) {
         const int c4 = cnt >> 2;
-        for (int i = threadIdx.x; i < c4; i += BLOCK) reinterpret_cast<float4*>(s)[i] = __ldg(reinterpret_cast<const float4*>(g + base) + i);
-        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += BLOCK) s[i] = g[base + i];
+        for (int i = threadIdx.x; i < c4; i += BS) reinterpret_cast<float4*>(s)[i] = __ldg(reinterpret_cast<const float4*>(g + base) + i);
+        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += BS) s[i] = g[base + i];
     } else {
-        for (int i = threadIdx.x; i < cnt; i += BLOCK) s[i] = g[base + i];
+        for (int i = threadIdx.x; i < cnt; i += BS) s[i] = g[base + i];
     }
     __syncthreads();
     if ((int)threadIdx.x * W < cnt) {
@@ -85,10 +88,10 @@ template <int W, typename E> __device__ __forceinline__ void tile_load(E* s, con
     __syncthreads();
 }
 // `write` is per-thread: rows whose thread passes write=false keep their previous contents
-template <int W, typename E> __device__ __forceinline__ void tile_store(E* s, E* g, long long row0, int n, const E* reg, bool all_write, bool write) {
+template <int W, typename E, int BS = BLOCK> __device__ __forceinline__ void tile_store(E* s, E* g, long long row0, int n, const E* reg, bool all_write, bool write) {
     if (g == nullptr) return;
     const long long base = row0 * W;
-    const int cnt = (int)min((long long)BLOCK, (long long)n - row0) * W;
+    const int cnt = (int)min((long long)BS, (long long)n - row0) * W;
     if (!all_write) {   // masked rows: each thread writes its own row directly
         if (write && (int)threadIdx.x * W < cnt) {
 #pragma unroll
@@ -103,10 +106,10 @@ template <int W, typename E> __device__ __forceinline__ void tile_store(E* s, E*
     __syncthreads();
     if (sizeof(E) == 4 && ((uintptr_t)(g + base) & 15) == 0) {
         const int c4 = cnt >> 2;
-        for (int i = threadIdx.x; i < c4; i += BLOCK) reinterpret_cast<float4*>(g + base)[i] = reinterpret_cast<const float4*>(s)[i];
-        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += BLOCK) g[base + i] = s[i];
+        for (int i = threadIdx.x; i < c4; i += BS) reinterpret_cast<float4*>(g + base)[i] = reinterpret_cast<const float4*>(s)[i];
+        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += BS) g[base + i] = s[i];
     } else {
-        for (int i = threadIdx.x; i < cnt; i += BLOCK) g[base + i] = s[i];
+        for (int i = threadIdx.x; i < cnt; i += BS) g[base + i] = s[i];
     }
     __syncthreads();
 }
@@ -142,24 +145,31 @@ template <typename T, int NOBJ> __device__ __forceinline__ void store_state(cons
 // Distributions: reach.py:22-23,51-54; push.py:69-87; slide.py:23-24,73-91; pick_and_place.py:65-85; stack.py:94-119;
 // flip.py:63-80 (goal: uniform rotation, drawn from the device stream instead of scipy's unseeded global RNG).
 template <typename T, int TASK>
-__device__ __forceinline__ void env_reset(const EnvDev<T>& E, int i, uint32_t episode, const double* goal_ov, const double* obj_ov, T* q, T* qd, Obj<T>* ob, T* goal) {
+__device__ __forceinline__ void env_reset(const EnvDev<T>& E, int i, uint32_t episode, const double* goal_ov, const double* obj_ov, T* q, T* qd, Obj<T>* ob, T* goal,
+                                          const unsigned long long* seeds = nullptr) {
     constexpr int NOBJ = task_nobj(TASK);
     constexpr int G = task_goal_dim(TASK);
     const double neutral[ND] = {0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79, 0.00, 0.00};   // panda.py:45
 #pragma unroll
     for (int d = 0; d < ND; d++) { q[d] = (T)neutral[d]; qd[d] = T(0); }
-    Philox rng(E.seed, (unsigned long long)(E.id0 + i), episode);
+    // RNG stream: (handle seed, global env id, episode) -- or, for a seeded reset, the env's own seed alone, so that equal seeds
+    // give equal goals / placements whatever the env index (test/seed_test.py semantics)
+    Philox rng(seeds ? seeds[i] : E.seed, seeds ? 0xA5A5A5A5ull : (unsigned long long)(E.id0 + i), seeds ? 0u : episode);
+    const TaskParams& P = E.P;
     double g[6] = {0, 0, 0, 0, 0, 0}, op[6] = {0, 0, 0, 0, 0, 0};
-    if (TASK == TASK_REACH) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); g[2] = rng.uniform(0.0, 0.3); }
-    else if (TASK == TASK_PUSH) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); g[2] = 0.02; }
-    else if (TASK == TASK_SLIDE) { g[0] = rng.uniform(0.25, 0.55); g[1] = rng.uniform(-0.15, 0.15); g[2] = 0.03; }
-    else if (TASK == TASK_PICK_AND_PLACE) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); double z = rng.uniform(0.0, 0.2); if (rng.uniform() < 0.3) z = 0.0; g[2] = 0.02 + z; }
-    else if (TASK == TASK_STACK) { g[0] = rng.uniform(-0.15, 0.15); g[1] = rng.uniform(-0.15, 0.15); g[2] = 0.02; g[3] = g[0]; g[4] = g[1]; g[5] = 0.06; }
-    else { double a = rng.normal(), b = rng.normal(), c = rng.normal(), d = rng.normal(), nn = 1.0 / sqrt(a * a + b * b + c * c + d * d); g[0] = a * nn; g[1] = b * nn; g[2] = c * nn; g[3] = d * nn; }
+    const double z0 = TASK == TASK_SLIDE ? 0.03 : 0.02;         // object_size / 2: the height at which goals and objects sit on the table
+    if (TASK == TASK_FLIP) { double a = rng.normal(), b = rng.normal(), c = rng.normal(), d = rng.normal(), nn = 1.0 / sqrt(a * a + b * b + c * c + d * d); g[0] = a * nn; g[1] = b * nn; g[2] = c * nn; g[3] = d * nn; }
+    else {
+        g[0] = rng.uniform(P.goal_lo[0], P.goal_hi[0]); g[1] = rng.uniform(P.goal_lo[1], P.goal_hi[1]);
+        double z = (TASK == TASK_REACH || TASK == TASK_PICK_AND_PLACE) ? rng.uniform(P.goal_lo[2], P.goal_hi[2]) : 0.0;
+        if (TASK == TASK_PICK_AND_PLACE && rng.uniform() < 0.3) z = 0.0;                       // pick_and_place.py:74-76: 30 % of the goals lie on the table
+        g[2] = (TASK == TASK_REACH ? 0.0 : z0) + z;
+        if (TASK == TASK_STACK) { g[3] = g[0]; g[4] = g[1]; g[5] = 0.06; }                    // stack.py:102-108: both goals share the noise
+    }
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) {
-        op[3 * o] = rng.uniform(-0.15, 0.15); op[3 * o + 1] = rng.uniform(-0.15, 0.15);
-        op[3 * o + 2] = TASK == TASK_SLIDE ? 0.03 : (o == 1 ? 0.06 : 0.02);
+        op[3 * o] = rng.uniform(P.obj_lo[0], P.obj_hi[0]); op[3 * o + 1] = rng.uniform(P.obj_lo[1], P.obj_hi[1]);
+        op[3 * o + 2] = o == 1 ? 0.06 : z0;
     }
     if (goal_ov) {
 #pragma unroll
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
     if (mine) {
         T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         uint32_t ep = E.episode[i] + 1u;
-        env_reset<T, TASK>(E, i, ep, io.goal_override, io.object_override, q, qd, ob, goal);
+        env_reset<T, TASK>(E, i, ep, io.goal_override, io.object_override, q, qd, ob, goal, io.seeds);
         store_state<T, NOBJ>(E, i, q, qd, ob);
 #pragma unroll
         for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
@@ -258,33 +268,39 @@ template <int W, typename E> __device__ __forceinline__ void row_store(E* g, int
 
 // Dynamic shared memory per block: solver_slots() words per thread of solver state (Jx + contact records, word-interleaved), aliased with
 // the I/O row tile that is only live before and after the simulation phase.
+// Threads per block: 128, except where the solver slab of 128 envs would exceed the 227 kB a block may own (fp64 parity mode on the
+// two-object scene: 416 slots x 8 B x 128 = 426 kB) -- those run 32-env blocks.
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+template <typename T, int TASK> constexpr int step_block() { return (size_t)solver_slots(task_nobj(TASK)) * BLOCK * sizeof(T) <= SMEM_LIMIT ? BLOCK : 32; }
 template <typename T, int TASK, int CTRL> constexpr size_t step_smem_bytes() {
-    constexpr int O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
+    constexpr int O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL), BS = step_block<T, TASK>();
     constexpr int W = O > NA ? (O > G ? O : G) : (NA > G ? NA : G);
-    constexpr size_t solver = (size_t)solver_slots(task_nobj(TASK)) * BLOCK * sizeof(T), tile = (size_t)W * BLOCK * sizeof(float);
+    constexpr size_t solver = (size_t)solver_slots(task_nobj(TASK)) * BS * sizeof(T), tile = (size_t)W * BS * sizeof(float);
     return solver > tile ? solver : tile;
 }
 template <typename T, int TASK, int CTRL>
-__global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ EnvDev<T> E, const StepIO io) {
-    constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL);
+__global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __grid_constant__ EnvDev<T> E, const StepIO io) {
+    constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL), BS = step_block<T, TASK>();
+    static_assert(step_smem_bytes<T, TASK, CTRL>() <= SMEM_LIMIT, "solver slab exceeds the per-block shared memory of sm_100");
     extern __shared__ __align__(16) unsigned char s_raw[];
     float* s_io = reinterpret_cast<float*>(s_raw);
     __shared__ double s_stats[5];
-    const long long row0 = (long long)blockIdx.x * BLOCK;
+    const long long row0 = (long long)blockIdx.x * BS;
     const bool mapped = E.perm != nullptr;               // launch-uniform
     const int t = (int)row0 + threadIdx.x;
     const bool valid = t < (mapped ? E.tcount : E.n);
     const int i = (valid && mapped) ? E.perm[E.t0 + t] : t;
     if (threadIdx.x < 5) s_stats[threadIdx.x] = 0.0;
-    const bool first = io.s0 == 0, last = io.s1 == 20;      // launch-uniform
+    __syncthreads();                                     // s_stats is zeroed before any warp can atomicAdd into it
+    const bool first = io.s0 == 0, last = io.s1 == E.P.nsub;      // launch-uniform
     float act[NA];
-    if (first) { if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA>(s_io, io.actions, row0, E.n, act); }
+    if (first) { if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA, float, BS>(s_io, io.actions, row0, E.n, act); }
     float obs[O], ag[G], dg[G], reward = 0.0f;
     unsigned char term = 0, trunc = 0;
     if (valid) {
         T q[ND], qd[ND], goal[6], target[ND]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         Contacts<T> C;
-        C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BLOCK;
+        C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BS;
         load_state<T, NOBJ>(E, i, q, qd, ob, goal);
         if (!first) {
 #pragma unroll
@@ -295,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
         if (first && io.target_quat) row_load<4>(io.target_quat, i, tquat);
         const long long clk0 = E.dbg ? clock64() : 0;
         env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, (first && io.target_quat) ? tquat : nullptr, obs, ag, dg, reward, term, C, sched_key,
-                                target, io.s0, io.s1);
+                                target, io.s0, io.s1, E.P.nsub, E.P.thr32);
         if (E.dbg) { E.dbg[2 * (size_t)(E.t0 + t)] = clock64() - clk0; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); E.dbg[2 * (size_t)(E.t0 + t) + 1] = (long long)sched_key | ((long long)smid << 16); }
         if (last) {
             int steps = E.steps[i] + 1;
@@ -330,9 +346,9 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
     if (mapped) {
         if (valid) { row_store<O>(io.obs, i, obs); row_store<G>(io.ag, i, ag); row_store<G>(io.dg, i, dg); }
     } else {
-        tile_store<O>(s_io, io.obs, row0, E.n, obs, true, valid);
-        tile_store<G>(s_io, io.ag, row0, E.n, ag, true, valid);
-        tile_store<G>(s_io, io.dg, row0, E.n, dg, true, valid);
+        tile_store<O, float, BS>(s_io, io.obs, row0, E.n, obs, true, valid);
+        tile_store<G, float, BS>(s_io, io.ag, row0, E.n, ag, true, valid);
+        tile_store<G, float, BS>(s_io, io.dg, row0, E.n, dg, true, valid);
     }
     if (valid) {
         if (io.reward) io.reward[i] = reward;
@@ -344,39 +360,113 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ Env
 }
 
 // ---------------------------------------------------------------------------------------------- raw state exchange / IK
-template <typename T, int TASK>
-__global__ void __launch_bounds__(BLOCK) get_state_kernel(const __grid_constant__ EnvDev<T> E, double* out) {
-    constexpr int NOBJ = task_nobj(TASK), G = task_goal_dim(TASK), SD = 18 + 13 * NOBJ + G + 1;
+// rows [q(9) qd(9) | per object pos3 quat4 lin3 ang3 | goal(G) | episode step] in float64; nobj / G are runtime (task and bare handles)
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) get_state_kernel(const __grid_constant__ EnvDev<T> E, int nobj, int G, double* out) {
+    const int SD = 18 + 13 * nobj + G + 1;
     const int i = blockIdx.x * BLOCK + threadIdx.x;
     if (i >= E.n) return;
     double* r = out + (size_t)i * SD; const int n = E.n;
     for (int d = 0; d < ND; d++) { r[d] = E.q[d * n + i]; r[9 + d] = E.qd[d * n + i]; }
-    for (int k = 0; k < 13 * NOBJ; k++) r[18 + k] = E.obj[(size_t)k * n + i];
-    for (int k = 0; k < G; k++) r[18 + 13 * NOBJ + k] = E.goal[k * n + i];
+    for (int k = 0; k < 13 * nobj; k++) r[18 + k] = E.obj[(size_t)k * n + i];
+    for (int k = 0; k < G; k++) r[18 + 13 * nobj + k] = E.goal[k * n + i];
     r[SD - 1] = E.steps[i];
 }
-template <typename T, int TASK>
-__global__ void __launch_bounds__(BLOCK) set_state_kernel(const __grid_constant__ EnvDev<T> E, const double* in, const unsigned char* mask) {
-    constexpr int NOBJ = task_nobj(TASK), G = task_goal_dim(TASK), SD = 18 + 13 * NOBJ + G + 1;
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) set_state_kernel(const __grid_constant__ EnvDev<T> E, int nobj, int G, const double* in, const unsigned char* mask) {
+    const int SD = 18 + 13 * nobj + G + 1;
     const int i = blockIdx.x * BLOCK + threadIdx.x;
     if (i >= E.n || (mask && !mask[i])) return;
     const double* r = in + (size_t)i * SD; const int n = E.n;
     for (int d = 0; d < ND; d++) { E.q[d * n + i] = (T)r[d]; E.qd[d * n + i] = (T)r[9 + d]; }
-    for (int k = 0; k < 13 * NOBJ; k++) E.obj[(size_t)k * n + i] = (T)r[18 + k];
-    for (int k = 0; k < G; k++) E.goal[k * n + i] = (T)r[18 + 13 * NOBJ + k];
+    for (int k = 0; k < 13 * nobj; k++) E.obj[(size_t)k * n + i] = (T)r[18 + k];
+    for (int k = 0; k < G; k++) E.goal[k * n + i] = (T)r[18 + 13 * nobj + k];
     E.steps[i] = (int)r[SD - 1];
 }
+// calculateInverseKinematics (pybullet.py:479-497) on `link` from the current joint state: target [n,3] + quaternion [n,4] (normalised
+// here; the reference's KAT test/pybullet_test.py:265 passes an un-normalised one) -> 9 joint values.  link 11 with out7 != 0 is the
+// env path's fixed instance (ik_ee, 7 arm angles per row).
 template <typename T>
-__global__ void __launch_bounds__(BLOCK) ik_kernel(const __grid_constant__ EnvDev<T> E, const double* pos, const double* quat, double* out) {
+__global__ void __launch_bounds__(BLOCK) ik_kernel(const __grid_constant__ EnvDev<T> E, int link, const double* pos, const double* quat, double* out, int out7) {
     const int i = blockIdx.x * BLOCK + threadIdx.x;
     if (i >= E.n) return;
-    T q[ND], tq[4], o[7];
+    T q[ND], tq[4], o[ND];
     for (int d = 0; d < ND; d++) q[d] = E.q[d * E.n + i];
     double nn = 0; for (int k = 0; k < 4; k++) nn += quat[(size_t)i * 4 + k] * quat[(size_t)i * 4 + k];
     nn = 1.0 / sqrt(nn);
     for (int k = 0; k < 4; k++) tq[k] = (T)(quat[(size_t)i * 4 + k] * nn);
-    ik_ee(E.M, q, mk<T>((T)pos[(size_t)i * 3], (T)pos[(size_t)i * 3 + 1], (T)pos[(size_t)i * 3 + 2]), tq, o);
-    for (int d = 0; d < 7; d++) out[(size_t)i * 7 + d] = (double)o[d];
+    const V3<T> p = mk<T>((T)pos[(size_t)i * 3], (T)pos[(size_t)i * 3 + 1], (T)pos[(size_t)i * 3 + 2]);
+    if (out7) { ik_ee(E.M, q, p, tq, o); for (int d = 0; d < 7; d++) out[(size_t)i * 7 + d] = (double)o[d]; }
+    else { ik_link(E.M, link, q, p, tq, o); for (int d = 0; d < ND; d++) out[(size_t)i * ND + d] = (double)o[d]; }
+}
+// getLinkState for any link 0..11 (pybullet.py:351-400): rows [pos3 quat4 lin3 ang3] float64; pose from the link-transform cache
+// FK(q - qd dt), velocity from the fresh state rotated by the cached basis
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) link_state_kernel(const __grid_constant__ EnvDev<T> E, int link, double* out) {
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n) return;
+    T q[ND], qd[ND], qc[ND], qt[4];
+    for (int d = 0; d < ND; d++) { q[d] = E.q[d * E.n + i]; qd[d] = E.qd[d * E.n + i]; qc[d] = q[d] - qd[d] * Consts<T>::dt; }
+    V3<T> p, l, a;
+    link_state(E.M, link, q, qd, qc, p, qt, l, a);
+    double* r = out + (size_t)i * 13;
+    r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = qt[0]; r[4] = qt[1]; r[5] = qt[2]; r[6] = qt[3];
+    r[7] = l.x; r[8] = l.y; r[9] = l.z; r[10] = a.x; r[11] = a.y; r[12] = a.z;
+}
+
+// ---------------------------------------------------------------------------------------------- bare world (the sim facade without a task)
+// What the reference's PyBullet facade is when used directly (panda_gym/pybullet.py: loadURDF + create_box + control_joints + step;
+// its own tests test/pybullet_test.py:56-65,110-204 do exactly that): a robot whose nine motors are whatever
+// setJointMotorControlArray left them (after loadURDF: velocity motors, target 0, max impulse 1 -- SURVEY App. B.1), up to two
+// free bodies, optional table / ground plane, and `nsub` x stepSimulation per call.  One thread per world; same sub-step code as the
+// env path (env_substep) with the generic motor rows.
+constexpr int BARE_BLOCK = 32;
+template <typename T, int NOBJ> constexpr size_t bare_smem_bytes() { return (size_t)solver_slots(NOBJ) * BARE_BLOCK * sizeof(T); }
+template <typename T, int NOBJ>
+__global__ void __launch_bounds__(BARE_BLOCK) bare_step_kernel(const __grid_constant__ EnvDev<T> E, int nsub) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int i = blockIdx.x * BARE_BLOCK + threadIdx.x;
+    if (i >= E.n) return;
+    const int n = E.n;
+    T q[ND], qd[ND], goal[6], target[ND], mot[27]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+    Contacts<T> C;
+    C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BARE_BLOCK;
+    load_state<T, NOBJ>(E, i, q, qd, ob, goal);
+    Model<T> M = E.M;
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+        target[d] = E.target[d * n + i];
+        mot[d] = E.motor[(0 * ND + d) * (size_t)n + i]; mot[9 + d] = E.motor[(1 * ND + d) * (size_t)n + i]; mot[18 + d] = E.motor[(2 * ND + d) * (size_t)n + i];
+        M.max_imp[d] = E.motor[(3 * ND + d) * (size_t)n + i];
+    }
+    bool full_sweep = true, limits_active = false;
+    for (int s = 0; s < nsub; s++) env_substep<T, NOBJ, false, true>(M, E.S, q, qd, target, ob, C, full_sweep, limits_active, mot);
+    store_state<T, NOBJ>(E, i, q, qd, ob);
+    E.steps[i] += 1;
+}
+// motors of the worlds whose mask byte is set (NULL = all): rows [9][5] = position gain, velocity gain, target angle, target
+// velocity, max force (N or N m; the impulse limit per sub-step is force x dt)
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) set_motors_kernel(const __grid_constant__ EnvDev<T> E, const double* in, const unsigned char* mask) {
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n || (mask && !mask[i])) return;
+    const size_t n = E.n;
+    for (int d = 0; d < ND; d++) {
+        const double* r = in + ((size_t)i * ND + d) * 5;
+        E.motor[(0 * ND + d) * n + i] = (T)r[0]; E.motor[(1 * ND + d) * n + i] = (T)r[1]; E.target[d * n + i] = (T)r[2];
+        E.motor[(2 * ND + d) * n + i] = (T)r[3]; E.motor[(3 * ND + d) * n + i] = (T)(r[4] * (double)Consts<T>::dt);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(BLOCK) get_motors_kernel(const __grid_constant__ EnvDev<T> E, double* out) {
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= E.n) return;
+    const size_t n = E.n;
+    for (int d = 0; d < ND; d++) {
+        double* r = out + ((size_t)i * ND + d) * 5;
+        r[0] = E.motor[(0 * ND + d) * n + i]; r[1] = E.motor[(1 * ND + d) * n + i]; r[2] = E.target[d * n + i];
+        r[3] = E.motor[(2 * ND + d) * n + i]; r[4] = (double)E.motor[(3 * ND + d) * n + i] / (double)Consts<T>::dt;
+    }
 }
 
 // End-effector (link 11) pose from the CURRENT joint state (getLinkState with computeForwardKinematics, the fork's
@@ -405,10 +495,10 @@ template <typename E, int G> struct RewardTile {
     static constexpr int NV = RPT * G / V;                                     // 16-byte words per thread and array
 };
 template <typename E, int TASK, bool WANT_REWARD>
-__global__ void __launch_bounds__(256) reward_kernel(const E* __restrict__ ag, const E* __restrict__ dg, float* __restrict__ reward, unsigned char* __restrict__ success, long long m, int reward_type, int vec_ok) {
+__global__ void __launch_bounds__(256) reward_kernel(const E* __restrict__ ag, const E* __restrict__ dg, float* __restrict__ reward, unsigned char* __restrict__ success, long long m, int reward_type, int vec_ok, double threshold) {
     constexpr int G = task_goal_dim(TASK);
     using TL = RewardTile<E, G>;
-    const E thr = sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK);
+    const E thr = (E)threshold;                  // compared in the dtype of the distance (numpy casts the Python-float threshold to it)
     const long long groups = vec_ok ? m / TL::RPT : 0;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
         union { float4 v[TL::NV]; E e[TL::RPT * G]; } a, b;
@@ -443,9 +533,9 @@ __global__ void __launch_bounds__(256) reward_kernel(const E* __restrict__ ag, c
 template <typename E, int TASK>
 __global__ void __launch_bounds__(256) her_relabel_kernel(const E* __restrict__ next_ag, const E* __restrict__ dg, const long long* __restrict__ src,
                                                           const long long* __restrict__ goal_src, E* __restrict__ dg_out, E* __restrict__ ag_out,
-                                                          float* __restrict__ reward, long long m, int reward_type) {
+                                                          float* __restrict__ reward, long long m, int reward_type, double threshold) {
     constexpr int G = task_goal_dim(TASK);
-    const E thr = sizeof(E) == 4 ? (E)threshold_f32(TASK) : (E)threshold_f64(TASK);
+    const E thr = (E)threshold;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
         const long long s = src[j], gs = goal_src[j];
         const E* pg = gs >= 0 ? next_ag + gs * G : dg + s * G;
@@ -462,7 +552,6 @@ __global__ void __launch_bounds__(256) her_relabel_kernel(const E* __restrict__ 
 // host-side launchers, instantiated per task in panda_step_task.cu
 template <typename T, int TASK> void launch_step(const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st);
 template <typename T, int TASK> void launch_reset(const EnvDev<T>& E, const ResetIO& io, cudaStream_t st);
-template <typename T, int TASK> void launch_get_state(const EnvDev<T>& E, double* out, cudaStream_t st);
-template <typename T, int TASK> void launch_set_state(const EnvDev<T>& E, const double* in, const unsigned char* mask, cudaStream_t st);
+template <typename T> void launch_bare_step(const EnvDev<T>& E, int nobj, int nsub, cudaStream_t st);   // panda_bare.cu
 
 }  // namespace pg

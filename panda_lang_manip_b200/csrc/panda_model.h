@@ -74,6 +74,7 @@ template <typename T> Model<T> make_model(const double base[3]) {
         const LinkConst& J = kLinks[b < 7 ? b : b + 1];
         M.lo[b] = (T)J.lo; M.hi[b] = (T)J.hi; M.max_imp[b] = (T)(kJointForces[b] * dt);
     }
+    M.z7 = (T)kLinks[7].xyz[2];
     M.hz = (T)(kLinks[7].xyz[2] + kLinks[8].xyz[2]);
     M.eez = (T)(kLinks[7].xyz[2] + kEeZ);
     M.fa[0] = (T)1; M.fa[1] = (T)-1;

@@ -17,6 +17,15 @@ template <typename T> void scene_set_obj(Scene<T>& S, int o, int shape, double h
         S.Ic[o][0] = S.Ic[o][1] = (T)(mass / 12 * h * h + mass / 4 * r * r); S.Ic[o][2] = (T)(mass / 2 * r * r);
     }
 }
+template <typename T, typename U> Scene<T> scene_cast(const Scene<U>& A) {
+    Scene<T> S;
+    S.nobj = A.nobj;
+    for (int o = 0; o < MAXOBJ; o++) { S.shape[o] = A.shape[o]; S.mass[o] = (T)A.mass[o]; S.mu[o] = (T)A.mu[o]; for (int k = 0; k < 3; k++) { S.half[o][k] = (T)A.half[o][k]; S.Ic[o][k] = (T)A.Ic[o][k]; } }
+    S.table_x0 = (T)A.table_x0; S.table_x1 = (T)A.table_x1; S.table_y0 = (T)A.table_y0; S.table_y1 = (T)A.table_y1;
+    for (int b = 0; b < 3; b++) { S.rb_mu[b] = (T)A.rb_mu[b]; for (int k = 0; k < 3; k++) { S.rb_c[b][k] = (T)A.rb_c[b][k]; S.rb_h[b][k] = (T)A.rb_h[b][k]; } }
+    S.margin = (T)A.margin; S.margin_grasp = (T)A.margin_grasp; S.ground_z = (T)A.ground_z; S.table_mu = (T)A.table_mu; S.soft_erp = (T)A.soft_erp; S.soft_cfm = (T)A.soft_cfm;
+    return S;
+}
 template <typename T> Scene<T> make_scene(int task) {
     Scene<T> S;
     memset(&S, 0, sizeof S);

@@ -132,15 +132,14 @@ class PandaVecEnv:
 
     # -- snapshots / raw state ---------------------------------------------------------------------------------------
     def save_state(self) -> int:
+        """Stream-ordered snapshot (one device-to-device copy on the current stream, no synchronisation)."""
         import ctypes
-        torch.cuda.current_stream(self.device).synchronize()
         sid = ctypes.c_int()
-        _lib.check(self.lib.pg_save_state(self._h, ctypes.byref(sid)))
+        _lib.check(self.lib.pg_save_state_async(self._h, ctypes.byref(sid), self._stream()))
         return sid.value
 
     def restore_state(self, state_id: int) -> None:
-        torch.cuda.current_stream(self.device).synchronize()
-        _lib.check(self.lib.pg_restore_state(self._h, int(state_id)))
+        _lib.check(self.lib.pg_restore_state_async(self._h, int(state_id), self._stream()))
 
     def remove_state(self, state_id: int) -> None:
         _lib.check(self.lib.pg_remove_state(self._h, int(state_id)))
@@ -186,11 +185,24 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_set_state(self._h, _ptr(s), _ptr(m), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
-    def inverse_kinematics(self, position, orientation) -> torch.Tensor:
+    def inverse_kinematics(self, position, orientation, link: Optional[int] = None) -> torch.Tensor:
+        """calculateInverseKinematics from the current joint state.  ``link=None``: the env path's link-11 solve, [N,7] arm angles;
+        ``link=k``: PyBullet.inverse_kinematics(body, k, ...) for any link 0..11, all nine joint values [N,9]."""
         p = torch.as_tensor(position, dtype=torch.float64, device=self.device).reshape(self.num_envs, 3).contiguous()
         o = torch.as_tensor(orientation, dtype=torch.float64, device=self.device).reshape(self.num_envs, 4).contiguous()
-        out = torch.empty((self.num_envs, 7), dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.pg_inverse_kinematics(self._h, _ptr(p), _ptr(o), _ptr(out), self._stream()))
+        if link is None:
+            out = torch.empty((self.num_envs, 7), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.pg_inverse_kinematics(self._h, _ptr(p), _ptr(o), _ptr(out), self._stream()))
+        else:
+            out = torch.empty((self.num_envs, 9), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.pg_inverse_kinematics_link(self._h, int(link), _ptr(p), _ptr(o), _ptr(out), self._stream()))
+        return out
+
+    def link_state(self, link: int) -> torch.Tensor:
+        """[N,13] float64 = getLinkState(link, computeLinkVelocity=1): CoM-frame position, quaternion (x,y,z,w), linear and angular
+        velocity of link 0..11, with pybullet's one-sub-step-stale link-transform cache."""
+        out = torch.empty((self.num_envs, 13), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.pg_get_link_state(self._h, int(link), _ptr(out), self._stream()))
         return out
 
     def ee_pose(self) -> torch.Tensor:
