@@ -20,7 +20,7 @@
  * Pinned by tests/test_oracle_kat.py against test/pybullet_test.py:34,:64,:135,:152,:169,:186,
  * :203,:265.  Everything involving contact is "parity unpinned" (no golden vectors exist).
  *
- * Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/Makefile).  -ffp-contract=off matters:
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -shared -fPIC (oracle/Makefile).  -ffp-contract=off matters:
  * the float32 reward arithmetic must not be fused.
  */
 #include "panda_oracle.h"
@@ -36,6 +36,7 @@
 #define DT (1.0 / 500.0)
 #define GRAV 9.81
 #define PI 3.14159265358979323846
+#define GROUND_Z (-0.4)   /* create_plane(z_offset=-0.4) in every task (reach.py:29 ...) */
 
 /* ------------------------------------------------------------------ small linear algebra */
 typedef double V3[3];
@@ -161,7 +162,7 @@ struct PoSim {
     double q[ND], qd[ND], qc[ND];
     double m_kp[ND], m_kd[ND], m_tq[ND], m_tv[ND], m_maximp[ND];
     int nobj; Obj obj[MAXOBJ];
-    double table_x0, table_x1, table_y0, table_y1;
+    double table_x0, table_x1, table_y0, table_y1, ground_z;   /* table top (z = 0) rectangle (empty: x0 > x1), ground plane height (-1e30: none) */
     int last_contacts, last_robot_contacts, last_iters;
     /* scratch of the last forward-dynamics pass (positions at the start of the sub-step) */
     double E[NL][9], r[NL][3], Rw[NL][9], pw[NL][3], S[NL][6];
@@ -348,7 +349,8 @@ PoSim *po_create(int task, double bx, double by, double bz) {
     s->task = task; v3set(s->base, bx, by, bz);
     for (int d = 0; d < ND; d++) { s->m_kp[d] = 0; s->m_kd[d] = 1; s->m_maximp[d] = 1.0; } /* loadURDF default velocity motors (App. B.1) */
     /* table top rectangle (pybullet.py:741-771; slide.py:33) */
-    s->table_x0 = -0.85; s->table_x1 = 0.25; s->table_y0 = -0.35; s->table_y1 = 0.35;
+    s->table_x0 = -0.85; s->table_x1 = 0.25; s->table_y0 = -0.35; s->table_y1 = 0.35; s->ground_z = GROUND_Z;
+    if (task == PO_BARE) { s->table_x0 = 1; s->table_x1 = -1; s->table_y0 = 1; s->table_y1 = -1; s->ground_z = -1e30; }   /* PyBullet() alone: no plane, no table */
     switch (task) {
     case PO_PUSH: case PO_PICK_AND_PLACE: case PO_FLIP:
         s->nobj = 1; obj_init(&s->obj[0], SH_BOX, 0.02, 0.02, 0.02, 1.0, 0.5); s->obj[0].pos[2] = 0.02; break;
@@ -367,6 +369,18 @@ int po_add_box(PoSim *s, double hx, double hy, double hz, double mass, const dou
     if (s->nobj >= MAXOBJ) return -1;
     obj_init(&s->obj[s->nobj], SH_BOX, hx, hy, hz, mass, 0.5); v3cpy(s->obj[s->nobj].pos, pos);
     return s->nobj++;
+}
+/* create_table / create_plane of a bare world (pybullet.py:726-771): NULL removes the surface */
+void po_set_static(PoSim *s, const double *table_rect, const double *ground_z) {
+    if (table_rect) { s->table_x0 = table_rect[0]; s->table_x1 = table_rect[1]; s->table_y0 = table_rect[2]; s->table_y1 = table_rect[3]; }
+    else { s->table_x0 = 1; s->table_x1 = -1; s->table_y0 = 1; s->table_y1 = -1; }
+    s->ground_z = ground_z ? *ground_z : -1e30;
+}
+/* raw joint state incl. the link-transform cache (test hook: getLinkState at an arbitrary state) */
+void po_set_joint_state(PoSim *s, const double *q, const double *qd, const double *qc) { memcpy(s->q, q, sizeof s->q); memcpy(s->qd, qd, sizeof s->qd); memcpy(s->qc, qc, sizeof s->qc); }
+void po_set_object_shape(PoSim *s, int o, int shape, double hx, double hy, double hz, double mass, double mu) {
+    Obj keep = s->obj[o]; obj_init(&s->obj[o], shape, hx, hy, hz, mass, mu);
+    v3cpy(s->obj[o].pos, keep.pos); memcpy(s->obj[o].quat, keep.quat, sizeof keep.quat); v3cpy(s->obj[o].lin, keep.lin); v3cpy(s->obj[o].ang, keep.ang);
 }
 void po_destroy(PoSim *s) { free(s); }
 int po_num_objects(const PoSim *s) { return s->nobj; }
@@ -508,7 +522,6 @@ void po_inverse_kinematics(const PoSim *s, int link, const double pos[3], const 
 #define MAXC_TWO_OBJECTS 22
 #define CONTACT_ERP 0.2
 #define LINEAR_SLOP 1e-5
-#define GROUND_Z (-0.4)
 #define TABLE_MU 0.5
 #define FINGER_MU 1.0
 #define HAND_MU 0.5
@@ -627,7 +640,7 @@ static void collect_contacts(PoSim *s, const double *gv) {
         const Obj *ob = &s->obj[o]; double R[9]; quat_to_R(R, ob->quat);
         for (int k = 0; k < 8; k++) {
             double v[3], P[3]; obj_vertex(ob, k, v); m3mulv(P, R, v); v3add(P, P, ob->pos);
-            double plane = over_table(s, P) && P[2] > -0.05 ? 0.0 : GROUND_Z;
+            double plane = over_table(s, P) && P[2] > -0.05 ? 0.0 : s->ground_z;
             double d = P[2] - plane;
             if (d < CONTACT_MARGIN) add_contact(s, gv, P, up, d, -1, o, -1, -1, ob->mu * TABLE_MU, 0);
         }

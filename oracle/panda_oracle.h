@@ -33,6 +33,9 @@ typedef struct PoSim PoSim;
 /* ---- L1: sim facade (mirrors panda_gym/pybullet.py) ---- */
 PoSim *po_create(int task, double base_x, double base_y, double base_z);
 void po_destroy(PoSim *s);
+void po_set_static(PoSim *s, const double *table_rect, const double *ground_z); /* pybullet.py:726-771 create_plane / create_table; NULL = absent */
+void po_set_joint_state(PoSim *s, const double *q, const double *qd, const double *qc);
+void po_set_object_shape(PoSim *s, int obj, int shape, double hx, double hy, double hz, double mass, double mu);
 int po_num_objects(const PoSim *s);
 int po_add_box(PoSim *s, double hx, double hy, double hz, double mass, const double pos[3]); /* pybullet.py:531-582 create_box */
 void po_step(PoSim *s, int n_substeps);                        /* pybullet.py:52-55 */

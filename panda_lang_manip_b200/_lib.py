@@ -21,7 +21,8 @@ SYMBOLS = [
     "pg_create", "pg_destroy", "pg_dims", "pg_reset", "pg_step", "pg_step_oriented", "pg_set_action_scale", "pg_step_host", "pg_host_pin", "pg_host_unpin", "pg_compute_reward", "pg_is_success",
     "pg_compute_reward_host", "pg_is_success_host", "pg_her_relabel", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_get_ee_pose", "pg_create_bare", "pg_set_motors", "pg_get_motors", "pg_sim_step", "pg_inverse_kinematics_link", "pg_get_link_state",
-    "pg_save_state_async", "pg_restore_state_async", "pg_host_stage_allocations", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
+    "pg_save_state_async", "pg_restore_state_async", "pg_host_stage_allocations", "pg_reset_seeded", "pg_set_task_params", "pg_set_substeps",
+    "pg_compute_reward_t", "pg_is_success_t", "pg_her_relabel_t", "pg_compute_reward_host_t", "pg_is_success_host_t", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
 _lib = None
@@ -77,6 +78,15 @@ def load() -> ctypes.CDLL:
     lib.pg_save_state_async.argtypes = [vp, pi, vp]
     lib.pg_restore_state_async.argtypes = [vp, c_int, vp]
     lib.pg_host_stage_allocations.restype = c_ll
+    cd = ctypes.c_double
+    lib.pg_reset_seeded.argtypes = [vp] * 10
+    lib.pg_set_task_params.argtypes = [vp, cd, vp, vp, vp, vp]
+    lib.pg_set_substeps.argtypes = [vp, c_int]
+    lib.pg_compute_reward_t.argtypes = [c_int, c_int, cd, vp, vp, vp, c_ll, c_int, vp]
+    lib.pg_is_success_t.argtypes = [c_int, cd, vp, vp, vp, c_ll, c_int, vp]
+    lib.pg_her_relabel_t.argtypes = [c_int, c_int, cd, vp, vp, vp, vp, vp, vp, vp, c_ll, c_int, vp]
+    lib.pg_compute_reward_host_t.argtypes = [c_int, c_int, cd, vp, vp, vp, c_ll, c_int, c_int]
+    lib.pg_is_success_host_t.argtypes = [c_int, cd, vp, vp, vp, c_ll, c_int, c_int]
     lib.pg_debug_schedule.argtypes = [vp, vp, vp]
     lib.pg_debug_timing.argtypes = [vp, vp]
     lib.pg_diverged.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]

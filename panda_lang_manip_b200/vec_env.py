@@ -11,6 +11,7 @@ import torch
 
 from . import _lib
 
+DEFAULT_THRESHOLD = {"reach": 0.05, "push": 0.05, "slide": 0.05, "pick_and_place": 0.05, "stack": 0.1, "flip": 0.2}   # tasks/*.py distance_threshold defaults
 MAX_EPISODE_STEPS = {"reach": 50, "push": 50, "slide": 50, "pick_and_place": 50, "stack": 100, "flip": 50}  # panda_gym/__init__.py
 
 
@@ -23,11 +24,13 @@ class PandaVecEnv:
 
     Args mirror the reference constructors (panda_gym/envs/panda_tasks.py): ``reward_type`` "sparse"|"dense",
     ``control_type`` "ee"|"joints".  ``env_id_offset`` is the global index of env 0 (sharded runs), ``precision`` "f32"
-    (product path) or "f64" (parity debugging).
+    (product path) or "f64" (parity debugging).  ``n_substeps`` is PyBullet(n_substeps) (pybullet.py:26); ``distance_threshold`` and the
+    ``*_range_low/high`` noise boxes are the task constructors' keyword arguments (tasks/*.py __init__), see ``set_task_params``.
     """
 
     def __init__(self, task: str, num_envs: int, reward_type: str = "sparse", control_type: str = "ee", device: int = 0,
-                 seed: int = 0, env_id_offset: int = 0, precision: str = "f32", auto_reset: bool = True) -> None:
+                 seed: int = 0, env_id_offset: int = 0, precision: str = "f32", auto_reset: bool = True, n_substeps: int = 20,
+                 distance_threshold: Optional[float] = None, goal_range_low=None, goal_range_high=None, obj_range_low=None, obj_range_high=None) -> None:
         import ctypes
         if not torch.cuda.is_available():
             raise _lib.PandaB200Error("PandaVecEnv needs a CUDA device: the B200 kernels are the only implementation")
@@ -40,6 +43,12 @@ class PandaVecEnv:
                                       int(seed) & (2**64 - 1), int(env_id_offset), _lib.PRECISION[precision], ctypes.byref(h)))
         self._h = h
         self._pinned = {}
+        self.distance_threshold = DEFAULT_THRESHOLD[task]
+        self.n_substeps = 20
+        if int(n_substeps) != 20:
+            self.set_substeps(n_substeps)
+        if any(v is not None for v in (distance_threshold, goal_range_low, goal_range_high, obj_range_low, obj_range_high)):
+            self.set_task_params(distance_threshold, goal_range_low, goal_range_high, obj_range_low, obj_range_high)
         d = [ctypes.c_int() for _ in range(5)]
         _lib.check(self.lib.pg_dims(h, *[ctypes.byref(x) for x in d]))
         self.obs_dim, self.goal_dim, self.action_dim, self.max_episode_steps, self.state_dim = [x.value for x in d]
@@ -87,14 +96,36 @@ class PandaVecEnv:
         return {"observation": self.obs, "achieved_goal": self.achieved_goal, "desired_goal": self.desired_goal}
 
     # -- RobotTaskEnv API, batched -----------------------------------------------------------------------------------
-    def reset(self, mask: Optional[torch.Tensor] = None, goals=None, object_positions=None) -> Dict[str, torch.Tensor]:
-        """Reset all envs (or those with mask != 0).  ``goals`` [N,G] / ``object_positions`` [N,3*n_obj] override the device sampler."""
+    def reset(self, mask: Optional[torch.Tensor] = None, goals=None, object_positions=None, seeds=None) -> Dict[str, torch.Tensor]:
+        """Reset all envs (or those with mask != 0).  ``goals`` [N,G] / ``object_positions`` [N,3*n_obj] override the device sampler;
+        ``seeds`` [N] (ints) is the batched ``reset(seed=k)``: each env's draws are keyed by its own seed only."""
         def f64(x):
             return None if x is None else torch.as_tensor(np.asarray(x, dtype=np.float64) if not torch.is_tensor(x) else x, dtype=torch.float64, device=self.device).contiguous()
         g, o = f64(goals), f64(object_positions)
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        _lib.check(self.lib.pg_reset(self._h, _ptr(m), _ptr(g), _ptr(o), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), self._stream()))
+        sd = None
+        if seeds is not None:       # uint64 bit patterns travel as int64
+            sd = torch.as_tensor(np.asarray(seeds.cpu() if torch.is_tensor(seeds) else seeds).astype(np.uint64).view(np.int64), device=self.device).reshape(self.num_envs).contiguous()
+        _lib.check(self.lib.pg_reset_seeded(self._h, _ptr(m), _ptr(sd), _ptr(g), _ptr(o), _ptr(self.obs), _ptr(self.achieved_goal), _ptr(self.desired_goal), self._stream()))
+        if sd is not None:
+            torch.cuda.current_stream(self.device).synchronize()
         return self._obs_dict()
+
+    def set_task_params(self, distance_threshold: Optional[float] = None, goal_range_low=None, goal_range_high=None, obj_range_low=None, obj_range_high=None) -> None:
+        """The reference task constructors' keyword arguments as kernel parameters: success / sparse-reward threshold, goal noise box
+        (3-vectors; what reach.py:21-23 / push.py:20-21 / slide.py:22-23 / pick_and_place.py:24-25 build from goal_range, goal_xy_range,
+        goal_z_range, goal_x_offset) and object xy noise box (2-vectors; obj_xy_range).  None keeps a value."""
+        def arr(x, k):
+            return None if x is None else np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)[:k])
+        thr = self.distance_threshold if distance_threshold is None else float(distance_threshold)
+        gl, gh, ol, oh = arr(goal_range_low, 3), arr(goal_range_high, 3), arr(obj_range_low, 2), arr(obj_range_high, 2)
+        _lib.check(self.lib.pg_set_task_params(self._h, thr, *[None if a is None else a.ctypes.data for a in (gl, gh, ol, oh)]))
+        self.distance_threshold = thr
+
+    def set_substeps(self, n_substeps: int) -> None:
+        """PyBullet(n_substeps) (pybullet.py:26): stepSimulation calls per env step."""
+        _lib.check(self.lib.pg_set_substeps(self._h, int(n_substeps)))
+        self.n_substeps = int(n_substeps)
 
     def set_action_scale(self, ee_scale: float = 0.05, finger_scale: float = 0.2) -> None:
         """Action scaling of Panda.set_action (panda.py:65,81); the fork's panda_cartesian robot uses (1.0, 1.0)."""
@@ -125,10 +156,10 @@ class PandaVecEnv:
         return {"observation": hb["obs"], "achieved_goal": hb["ag"], "desired_goal": hb["dg"]}, hb["rew"], hb["term"], hb["trunc"], {"is_success": hb["term"]}
 
     def compute_reward(self, achieved_goal: torch.Tensor, desired_goal: torch.Tensor, info=None) -> torch.Tensor:
-        return compute_reward(self.task, self.reward_type, achieved_goal, desired_goal)
+        return compute_reward(self.task, self.reward_type, achieved_goal, desired_goal, threshold=self.distance_threshold)
 
     def is_success(self, achieved_goal: torch.Tensor, desired_goal: torch.Tensor) -> torch.Tensor:
-        return is_success(self.task, achieved_goal, desired_goal)
+        return is_success(self.task, achieved_goal, desired_goal, threshold=self.distance_threshold)
 
     # -- snapshots / raw state ---------------------------------------------------------------------------------------
     def save_state(self) -> int:
@@ -240,25 +271,28 @@ def _goal_args(task: str, achieved_goal: torch.Tensor, desired_goal: torch.Tenso
     return a, d, (1 if dt == torch.float64 else 0), a.shape[:-1], a.numel() // g
 
 
-def compute_reward(task: str, reward_type: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor) -> torch.Tensor:
-    """Vectorised Task.compute_reward (tasks/<task>.py, utils.py:4-30) for HER relabelling: float32 rewards, bit-exact vs numpy."""
+def compute_reward(task: str, reward_type: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor, threshold: Optional[float] = None) -> torch.Tensor:
+    """Vectorised Task.compute_reward (tasks/<task>.py, utils.py:4-30) for HER relabelling: float32 rewards, bit-exact vs numpy.
+    ``threshold``: the task's distance_threshold (default: the reference's 0.05 / 0.1 Stack / 0.2 Flip)."""
     a, d, code, lead, m = _goal_args(task, achieved_goal, desired_goal)
     out = torch.empty(lead, dtype=torch.float32, device=a.device)
+    thr = DEFAULT_THRESHOLD[task] if threshold is None else float(threshold)
     with torch.cuda.device(a.device):
-        _lib.check(_lib.load().pg_compute_reward(_lib.TASKS[task], _lib.REWARD[reward_type], _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
+        _lib.check(_lib.load().pg_compute_reward_t(_lib.TASKS[task], _lib.REWARD[reward_type], thr, _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
     return out
 
 
-def is_success(task: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor) -> torch.Tensor:
+def is_success(task: str, achieved_goal: torch.Tensor, desired_goal: torch.Tensor, threshold: Optional[float] = None) -> torch.Tensor:
     a, d, code, lead, m = _goal_args(task, achieved_goal, desired_goal)
     out = torch.empty(lead, dtype=torch.uint8, device=a.device)
+    thr = DEFAULT_THRESHOLD[task] if threshold is None else float(threshold)
     with torch.cuda.device(a.device):
-        _lib.check(_lib.load().pg_is_success(_lib.TASKS[task], _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
+        _lib.check(_lib.load().pg_is_success_t(_lib.TASKS[task], thr, _ptr(a), _ptr(d), _ptr(out), m, code, torch.cuda.current_stream(a.device).cuda_stream))
     return out.bool()
 
 
 def her_relabel(task: str, reward_type: str, next_achieved_goal: torch.Tensor, desired_goal: torch.Tensor, src: torch.Tensor, goal_src: torch.Tensor,
-                return_achieved: bool = False):
+                return_achieved: bool = False, threshold: Optional[float] = None):
     """HER relabelling fused with compute_reward, on the device (the learner-side caller of the step path: the reference's
     examples/train_push.py:1-12 sets up stable-baselines3's HerReplayBuffer, which does this with a numpy gather and
     ``env.compute_reward``).  ``next_achieved_goal`` / ``desired_goal`` are the replay buffer's goal arrays flattened to [R, G];
@@ -281,7 +315,8 @@ def her_relabel(task: str, reward_type: str, next_achieved_goal: torch.Tensor, d
     ag_out = torch.empty((m, g), dtype=dt, device=a.device) if return_achieved else None
     rew = torch.empty((m,), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        _lib.check(_lib.load().pg_her_relabel(_lib.TASKS[task], _lib.REWARD[reward_type], _ptr(a), _ptr(d), _ptr(s_), _ptr(gs), _ptr(new_dg), _ptr(ag_out), _ptr(rew),
+        _lib.check(_lib.load().pg_her_relabel_t(_lib.TASKS[task], _lib.REWARD[reward_type], DEFAULT_THRESHOLD[task] if threshold is None else float(threshold),
+                                                _ptr(a), _ptr(d), _ptr(s_), _ptr(gs), _ptr(new_dg), _ptr(ag_out), _ptr(rew),
                                               m, 1 if dt == torch.float64 else 0, torch.cuda.current_stream(a.device).cuda_stream))
     return (new_dg, rew, ag_out) if return_achieved else (new_dg, rew)
 

@@ -36,4 +36,7 @@ def hostcheck():
     lib.hc_substeps.argtypes = [ci, vp, vp, vp, vp, ci]
     lib.hc_observe.argtypes = [ci] + [vp] * 6
     lib.hc_ik.argtypes = [ci] + [vp] * 5
+    lib.hc_link_state.argtypes = [ci, vp, ci, vp, vp, vp, vp]
+    lib.hc_ik_link.argtypes = [ci, vp, ci, vp, vp, vp, vp]
+    lib.hc_bare_steps.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, ci]
     return lib

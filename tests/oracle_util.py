@@ -49,6 +49,8 @@ def load_oracle():
         lib.po_save_state.argtypes = [vp, vp]; lib.po_restore_state.argtypes = [vp, vp]
         lib.po_last_num_contacts.argtypes = [vp]; lib.po_last_iterations.argtypes = [vp]
         lib.po_mass_matrix.argtypes = [vp, vp]
+        lib.po_set_static.argtypes = [vp, vp, vp]; lib.po_set_joint_state.argtypes = [vp, vp, vp, vp]
+        lib.po_set_object_shape.argtypes = [vp, ctypes.c_int, ctypes.c_int, D, D, D, D, D]
         for f in ("po_compute_reward_f32", "po_compute_reward_f64"):
             getattr(lib, f).argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_long]
         for f in ("po_is_success_f32", "po_is_success_f64"):

@@ -39,13 +39,15 @@ def _rollout(task, control, n_envs, steps, precision="f32", seed=0, action_scale
     oracles = [OracleEnv(task, control) for _ in range(n_envs)]
     ref0 = [oe.reset(goals[i], objs[i]) for i, oe in enumerate(oracles)]
     assert np.allclose(o0["observation"].cpu().numpy(), np.array([r[0] for r in ref0]), atol=1e-6)
-    errs = dict(q=0.0, qd=0.0, ee=0.0, obs=0.0, obj=0.0, rew=0, succ=0, q_env=np.zeros(n_envs), ee_env=np.zeros(n_envs), obj_env=np.zeros(n_envs))
+    errs = dict(q=0.0, qd=0.0, ee=0.0, obs=0.0, obj=0.0, rew=0, succ=0, rew_oracle=0, compared=0, q_env=np.zeros(n_envs), ee_env=np.zeros(n_envs), obj_env=np.zeros(n_envs))
     A = env.action_dim
+    thr = {"stack": 0.1, "flip": 0.2}.get(task, 0.05)
     for t in range(steps):
         a = (rng.uniform(-1, 1, (n_envs, A)) * action_scale).astype(np.float32)
         obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
         st = env.get_state().cpu().numpy()
-        obs_g, ag_g, rew_g, term_g = obs["observation"].cpu().numpy(), obs["achieved_goal"].cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy()
+        obs_g, ag_g, dg_g = obs["observation"].cpu().numpy(), obs["achieved_goal"].cpu().numpy(), obs["desired_goal"].cpu().numpy()
+        rew_g, term_g = rew.cpu().numpy(), term.cpu().numpy()
         for i, oe in enumerate(oracles):
             ob, ag, dg, r, s = oe.step(a[i])
             q, qd = oe.joints()
@@ -55,15 +57,22 @@ def _rollout(task, control, n_envs, steps, precision="f32", seed=0, action_scale
             for o in range(nobj):
                 eo = np.abs(st[i, 18 + 13 * o:18 + 13 * o + 7] - oe.object_state(o)[:7]).max()
                 errs["obj"] = max(errs["obj"], eo); errs["obj_env"][i] = max(errs["obj_env"][i], eo)
+            # reward / success of EVERY env at EVERY step, teacher-forced or free-running: bit-exact against the reference's arithmetic
+            # (numpy) on the float32 goals the kernel itself emitted ...
+            r_np, s_np = reward_np(task, "sparse", ag_g[i], dg_g[i])
+            errs["rew"] += int(np.float32(rew_g[i]).tobytes() != np.float32(r_np).tobytes()); errs["succ"] += int(bool(term_g[i]) != bool(s_np))
+            errs["compared"] += 1
+            # ... and against the oracle's own decision, unless the oracle's distance sits within 1 mm of the threshold (an fp32 state
+            # 1e-4 away from the fp64 one may legitimately fall on the other side there)
+            d_or = float(1 - np.dot(ag.astype(np.float64), dg.astype(np.float64)) ** 2) if task == "flip" else float(np.linalg.norm(ag.astype(np.float64) - dg.astype(np.float64)))
+            if abs(d_or - thr) > 1e-3:
+                errs["rew_oracle"] += int(bool(term_g[i]) != bool(s)) + int(float(rew_g[i]) != float(r))
             if teacher:     # per-step comparison: continue from the oracle's state
                 st[i, :9], st[i, 9:18] = q, qd
                 for o in range(nobj):
                     st[i, 18 + 13 * o:18 + 13 * o + 13] = oe.object_state(o)
         if teacher:
             env.set_state(torch.from_numpy(st))
-            # reward / success must be bit-exact on the GPU's own float32 goals
-            r_np, s_np = reward_np(task, "sparse", ag_g[i], obs["desired_goal"][i].cpu().numpy())
-            errs["rew"] += int(np.float32(rew_g[i]).tobytes() != np.float32(r_np).tobytes()); errs["succ"] += int(bool(term_g[i]) != bool(s_np))
     for oe in oracles:
         oe.close()
     env.close()
@@ -76,7 +85,7 @@ def test_reach_per_step_parity_f32(control):
     the oracle's state (fp32 kernels vs fp64 oracle), all envs, all steps."""
     e = _rollout("reach", control, n_envs=16, steps=50, precision="f32", seed=1, teacher=True)
     assert e["q"] < 1e-4 and e["ee"] < 1e-4, e
-    assert e["rew"] == 0 and e["succ"] == 0, e
+    assert e["compared"] == 16 * 50 and e["rew"] == 0 and e["succ"] == 0 and e["rew_oracle"] == 0, e
 
 
 @pytest.mark.parametrize("control", ["joints", "ee"])
@@ -87,7 +96,7 @@ def test_reach_free_running_parity_f32(control):
     e = _rollout("reach", control, n_envs=32, steps=50, precision="f32", seed=1)
     assert np.median(e["q_env"]) < 2e-5 and np.median(e["ee_env"]) < 2e-5, e
     assert (e["q_env"] < 1e-4).mean() >= 0.8 and (e["ee_env"] < 1e-4).mean() >= 0.8, e
-    assert e["q"] < 5e-3 and e["rew"] == 0 and e["succ"] == 0, e
+    assert e["q"] < 5e-3 and e["compared"] == 32 * 50 and e["rew"] == 0 and e["succ"] == 0 and e["rew_oracle"] == 0, e
 
 
 @pytest.mark.parametrize("control", ["joints", "ee"])
@@ -95,7 +104,7 @@ def test_reach_episode_parity_f64(control):
     """fp64 kernels vs the fp64 oracle, free-running: two independent formulations (CRBA+Cholesky+operational-space contacts vs
     ABA+impulse responses+generalized rows) agree to 1e-4 over whole episodes."""
     e = _rollout("reach", control, n_envs=8, steps=50, precision="f64", seed=2)
-    assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["rew"] == 0 and e["succ"] == 0, e
+    assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["compared"] == 8 * 50 and e["rew"] == 0 and e["succ"] == 0 and e["rew_oracle"] == 0, e
     assert np.median(e["q_env"]) < 2e-5, e
 
 
@@ -104,7 +113,7 @@ def test_contact_tasks_short_horizon(task):
     """Random actions, 25 steps free-running, fp32: typical env 2e-5 rad / 3e-4 m object pose, worst env 1e-3 rad / 2e-2 m (a tumbling object amplifies fp32 noise)."""
     e = _rollout(task, "ee", n_envs=8, steps=25, precision="f32", seed=3)
     assert np.median(e["q_env"]) < 2e-5 and e["q"] < 1e-3 and np.median(e["obj_env"]) < 3e-4 and e["obj"] < 2e-2, e
-    assert e["rew"] == 0 and e["succ"] == 0, e
+    assert e["compared"] == 8 * 25 and e["rew"] == 0 and e["succ"] == 0, e
 
 
 @pytest.mark.parametrize("task", ["push", "pick_and_place", "stack"])
@@ -112,6 +121,7 @@ def test_contact_tasks_per_step(task):
     """Per-step (teacher-forced) agreement on contact tasks: robot 1e-4, object pose (position, quaternion) 5e-4."""
     e = _rollout(task, "ee", n_envs=8, steps=25, precision="f32", seed=4, teacher=True)
     assert e["q"] < 1e-4 and e["ee"] < 1e-4 and e["obj"] < 5e-4 and np.median(e["obj_env"]) < 1e-4, e
+    assert e["compared"] == 8 * 25 and e["rew"] == 0 and e["succ"] == 0 and e["rew_oracle"] == 0, e
 
 
 @pytest.mark.parametrize("task,G", [("reach", 3), ("stack", 6)])

@@ -10,7 +10,7 @@ def test_dt():                      # test/pybullet_test.py:34  -- 20 sub-steps 
 
 def test_free_fall_velocity():      # test/pybullet_test.py:57-65
     s = OracleSim()
-    o = s.add_box([0.5, 0.5, 0.5], 1.0, [0.0, 0.0, 10.0])
+    o = s.add_box([0.5, 0.5, 0.5], 1.0, [0.0, 0.0, 0.0])     # as the reference: at the origin; a bare world has no plane to land on
     s.step()
     v, _ = s.base_velocity(o)
     assert np.allclose(v, [0.0, 0.0, -0.392], atol=1e-3)
