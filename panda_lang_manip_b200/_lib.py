@@ -79,7 +79,7 @@ def load() -> ctypes.CDLL:
     lib.pg_restore_state_async.argtypes = [vp, c_int, vp]
     lib.pg_host_stage_allocations.restype = c_ll
     cd = ctypes.c_double
-    lib.pg_reset_seeded.argtypes = [vp] * 10
+    lib.pg_reset_seeded.argtypes = [vp] * 9
     lib.pg_set_task_params.argtypes = [vp, cd, vp, vp, vp, vp]
     lib.pg_set_substeps.argtypes = [vp, c_int]
     lib.pg_compute_reward_t.argtypes = [c_int, c_int, cd, vp, vp, vp, c_ll, c_int, vp]

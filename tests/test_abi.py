@@ -68,3 +68,15 @@ def test_learner_side_helpers_import_and_sample_on_cpu():
     assert abs(rel.float().mean().item() - 0.8) < 0.02 and bool(((gi >= src) & (gi < start + T))[rel].all())
     with __import__("pytest").raises(p.PandaB200Error):       # no device here: the relabel kernel refuses CPU tensors, there is no fallback
         p.her_relabel("reach", "sparse", torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long))
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every entry point's ctypes argtypes list has as many entries as the header's declaration has parameters."""
+    from panda_lang_manip_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "panda_b200.h")).read(), flags=re.S)
+    lib = _lib.load()
+    for m in re.finditer(r"\b(pg_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        at = getattr(lib, name).argtypes
+        assert (at is None and n == 0) or (at is not None and len(at) == n), (name, n, at)
