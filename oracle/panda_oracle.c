@@ -893,6 +893,24 @@ void po_env_step_oriented(PoEnv *e, const float *action, const double *target_qu
     po_compute_reward_f32(e->task, e->reward, ag, dg, reward, 1);
 }
 
+/* batched forms for the test-suite's threaded / multi-process drivers: envs[i] steps with actions[i] */
+void po_env_step_batch(PoEnv **envs, int n, int na, int no, int ng, const float *actions, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated) {
+    for (int i = 0; i < n; i++) po_env_step(envs[i], actions + (size_t)i * na, obs + (size_t)i * no, ag + (size_t)i * ng, dg + (size_t)i * ng, reward + i, terminated + i);
+}
+/* full state of an env: q[9] qd[9] | per object pos3 quat4 lin3 ang3 | goal[G]  (the layout of pg_get_state without the step counter) */
+void po_env_set_full_state(PoEnv *e, const double *st) {
+    PoSim *s = e->sim; int g = goal_dim(e->task);
+    po_env_set_state(e, st, st + 9);
+    for (int o = 0; o < s->nobj; o++) { const double *p = st + 18 + 13 * o; po_set_base_pose(s, o, p, p + 3); po_set_base_velocity(s, o, p + 7, p + 10); }
+    memcpy(e->goal, st + 18 + 13 * s->nobj, g * sizeof(double));
+}
+void po_env_get_full_state(PoEnv *e, double *st) {
+    PoSim *s = e->sim; int g = goal_dim(e->task);
+    memcpy(st, s->q, sizeof s->q); memcpy(st + 9, s->qd, sizeof s->qd);
+    for (int o = 0; o < s->nobj; o++) { double *p = st + 18 + 13 * o; po_get_base_pose(s, o, p, p + 3); po_get_base_velocity(s, o, p + 7, p + 10); }
+    memcpy(st + 18 + 13 * s->nobj, e->goal, g * sizeof(double));
+}
+
 /* ------------------------------------------------------------------ CPU baseline driver (bench.py cpu_baseline / --impl reference)
  * Random-action rollout of one env, reset on success or at the TimeLimit (test/envs_test.py:6-14 loop), xorshift actions. */
 static double rnd01(unsigned long long *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return (double)(*s >> 11) / 9007199254740992.0; }

@@ -80,6 +80,9 @@ void po_env_step_oriented(PoEnv *e, const float *action, const double *target_qu
 void po_env_step(PoEnv *e, const float *action, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated);
 
 /* CPU baseline driver: random-action rollout of one env for n_steps env steps (reset on success / TimeLimit) */
+void po_env_step_batch(PoEnv **envs, int n, int na, int no, int ng, const float *actions, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated);
+void po_env_set_full_state(PoEnv *e, const double *st);
+void po_env_get_full_state(PoEnv *e, double *st);
 double po_bench_run(int task, int control, int n_steps, unsigned long long seed);
 
 /* ---- rewards (utils.py:4-30; tasks/ is_success / compute_reward) ---- */

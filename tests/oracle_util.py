@@ -49,6 +49,8 @@ def load_oracle():
         lib.po_save_state.argtypes = [vp, vp]; lib.po_restore_state.argtypes = [vp, vp]
         lib.po_last_num_contacts.argtypes = [vp]; lib.po_last_iterations.argtypes = [vp]
         lib.po_mass_matrix.argtypes = [vp, vp]
+        lib.po_env_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+        lib.po_env_set_full_state.argtypes = [vp, vp]; lib.po_env_get_full_state.argtypes = [vp, vp]
         lib.po_set_static.argtypes = [vp, vp, vp]; lib.po_set_joint_state.argtypes = [vp, vp, vp, vp]
         lib.po_set_object_shape.argtypes = [vp, ctypes.c_int, ctypes.c_int, D, D, D, D, D]
         for f in ("po_compute_reward_f32", "po_compute_reward_f64"):
@@ -168,6 +170,45 @@ class OracleEnv:
 
     def contacts(self):
         return self.lib.po_last_num_contacts(self.sim), self.lib.po_last_iterations(self.sim)
+
+    def set_full_state(self, st):
+        """q(9) qd(9) | per object pos3 quat4 lin3 ang3 | goal(G): a row of pg_get_state without its trailing step counter."""
+        st = np.ascontiguousarray(st, np.float64)
+        self.lib.po_env_set_full_state(self.h, P(st))
+
+    def full_state(self):
+        st = np.zeros(18 + 13 * NOBJ[self.task] + GOAL_DIM[self.task])
+        self.lib.po_env_get_full_state(self.h, P(st))
+        return st
+
+
+class OracleBatch:
+    """n oracle envs stepped together by one C call (po_env_step_batch); the scripted-policy drivers fork one of these per core."""
+
+    def __init__(self, task, n, control_type="ee"):
+        self.lib = load_oracle()
+        self.task, self.n = task, n
+        ct = 0 if control_type == "ee" else 1
+        self.handles = (ctypes.c_void_p * n)(*[self.lib.po_env_create(TASKS[task], ct, 0) for _ in range(n)])
+        self.na = (3 if control_type == "ee" else 7) + (0 if task in BLOCKED else 1)
+        self.no, self.ng = OBS_DIM[task], GOAL_DIM[task]
+        self.obs = np.zeros((n, self.no), np.float32); self.ag = np.zeros((n, self.ng), np.float32); self.dg = np.zeros((n, self.ng), np.float32)
+        self.rew = np.zeros(n, np.float32); self.term = np.zeros(n, np.uint8)
+
+    def reset(self, goals, objs):
+        for i in range(self.n):
+            g = np.ascontiguousarray(np.resize(np.asarray(goals[i], np.float64), 6)); o = np.ascontiguousarray(np.resize(np.asarray(objs[i], np.float64), 6))
+            self.lib.po_env_reset(self.handles[i], P(g), P(o), P(self.obs[i]), P(self.ag[i]), P(self.dg[i]))
+        return self.obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.float32)
+        self.lib.po_env_step_batch(self.handles, self.n, self.na, self.no, self.ng, P(a), P(self.obs), P(self.ag), P(self.dg), P(self.rew), P(self.term))
+        return self.obs, self.rew, self.term
+
+    def close(self):
+        for h in self.handles:
+            self.lib.po_env_destroy(h)
 
 
 def reward_np(task, reward_type, ag, dg):
