@@ -822,16 +822,19 @@ void po_is_success_f64(int task, const double *ag, const double *dg, unsigned ch
 }
 
 /* ------------------------------------------------------------------ env (core.py:229-289, panda.py, tasks/) */
-struct PoEnv { PoSim *sim; int task, control, reward, block_gripper; double goal[6]; };
+struct PoEnv { PoSim *sim; int task, control, reward, block_gripper, nsub; double goal[6]; float thr32; };
 static const double NEUTRAL[ND] = {0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79, 0.00, 0.00};
 static const double FORCES[ND] = {87.0, 87.0, 87.0, 87.0, 12.0, 120.0, 120.0, 170.0, 170.0};
 PoEnv *po_env_create(int task, int control, int reward) {
     PoEnv *e = (PoEnv *)calloc(1, sizeof(PoEnv));
     e->sim = po_create(task, -0.6, 0.0, 0.0); e->task = task; e->control = control; e->reward = reward;
     e->block_gripper = (task == PO_REACH || task == PO_PUSH || task == PO_SLIDE); /* panda_tasks.py:60,77,94 */
+    e->nsub = 20; e->thr32 = thr_f32(task);
     return e;
 }
 void po_env_destroy(PoEnv *e) { po_destroy(e->sim); free(e); }
+/* PyBullet(n_substeps) (pybullet.py:26) and the task's distance_threshold (tasks/reach.py:15 ...) */
+void po_env_set_params(PoEnv *e, int n_substeps, double distance_threshold) { e->nsub = n_substeps; e->thr32 = (float)distance_threshold; }
 PoSim *po_env_sim(PoEnv *e) { return e->sim; }
 int po_env_goal_dim(const PoEnv *e) { return goal_dim(e->task); }
 int po_env_action_dim(const PoEnv *e) { return (e->control == PO_CTRL_EE ? 3 : 7) + (e->block_gripper ? 0 : 1); }
@@ -887,10 +890,9 @@ void po_env_step_oriented(PoEnv *e, const float *action, const double *target_qu
     double w = e->block_gripper ? 0.0 : (s->q[7] + s->q[8]) + a[na - 1] * finger_scale;
     target[7] = target[8] = w / 2;
     for (int d = 0; d < ND; d++) po_control_joint(s, DOF_LINK[d], target[d], FORCES[d]);
-    po_step(s, 20);
+    po_step(s, e->nsub);
     env_obs(e, obs, ag, dg);
-    po_is_success_f32(e->task, ag, dg, terminated, 1);
-    po_compute_reward_f32(e->task, e->reward, ag, dg, reward, 1);
+    { float d = dist_f32(e->task, ag, dg); *terminated = d < e->thr32; *reward = e->reward == PO_REWARD_SPARSE ? -(d > e->thr32 ? 1.0f : 0.0f) : -d; }
 }
 
 /* batched forms for the test-suite's threaded / multi-process drivers: envs[i] steps with actions[i] */

@@ -68,6 +68,7 @@ void po_get_robot_box(int i, double out[8]);
 typedef struct PoEnv PoEnv;
 PoEnv *po_env_create(int task, int control_type, int reward_type);
 void po_env_destroy(PoEnv *e);
+void po_env_set_params(PoEnv *e, int n_substeps, double distance_threshold);
 PoSim *po_env_sim(PoEnv *e);
 int po_env_obs_dim(const PoEnv *e);
 int po_env_goal_dim(const PoEnv *e);

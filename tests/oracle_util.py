@@ -49,6 +49,7 @@ def load_oracle():
         lib.po_save_state.argtypes = [vp, vp]; lib.po_restore_state.argtypes = [vp, vp]
         lib.po_last_num_contacts.argtypes = [vp]; lib.po_last_iterations.argtypes = [vp]
         lib.po_mass_matrix.argtypes = [vp, vp]
+        lib.po_env_set_params.argtypes = [vp, ctypes.c_int, D]
         lib.po_env_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
         lib.po_env_set_full_state.argtypes = [vp, vp]; lib.po_env_get_full_state.argtypes = [vp, vp]
         lib.po_set_static.argtypes = [vp, vp, vp]; lib.po_set_joint_state.argtypes = [vp, vp, vp, vp]
@@ -122,10 +123,12 @@ class OracleSim:
 class OracleEnv:
     """RobotTaskEnv-level view of the oracle for one environment."""
 
-    def __init__(self, task, control_type="ee", reward_type="sparse"):
+    def __init__(self, task, control_type="ee", reward_type="sparse", n_substeps=20, distance_threshold=None):
         self.lib = load_oracle()
         self.task = task
         self.h = self.lib.po_env_create(TASKS[task], 0 if control_type == "ee" else 1, 0 if reward_type == "sparse" else 1)
+        if n_substeps != 20 or distance_threshold is not None:
+            self.lib.po_env_set_params(self.h, int(n_substeps), float({"stack": 0.1, "flip": 0.2}.get(task, 0.05) if distance_threshold is None else distance_threshold))
         self.sim = self.lib.po_env_sim(self.h)
         self.obs = np.zeros(OBS_DIM[task], np.float32)
         self.ag = np.zeros(GOAL_DIM[task], np.float32)

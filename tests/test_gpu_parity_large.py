@@ -1,0 +1,56 @@
+"""Oracle check AT BASELINE SIZE: the sorted / segmented / multi-stream path that every BASELINE-size run takes (thread -> env
+re-sort before each launch, a step cut into sub-step launches, env groups on their own streams) compared DIRECTLY with the oracle:
+in an auto-reset run past step 60 (episodes at every phase, contact states mixed), 256 random envs are pulled with pg_get_state, the
+whole batch is stepped once, and the oracle steps the same 256 states with the same actions."""
+import numpy as np
+import pytest
+
+from tests.oracle_util import GOAL_DIM, NOBJ, OracleEnv
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("task,control,n", [("reach", "joints", 65536), ("reach", "ee", 65536), ("pick_and_place", "ee", 32768), ("push", "ee", 65536), ("stack", "ee", 16384)])
+def test_baseline_size_step_matches_oracle(task, control, n):
+    import panda_lang_manip_b200 as p
+    env = p.PandaVecEnv(task, n, control_type=control, seed=5, auto_reset=True)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A, nobj, G = env.action_dim, NOBJ[task], GOAL_DIM[task]
+    for t in range(62):
+        a = torch.rand((n, A), device="cuda", generator=g) * 2 - 1
+        if task != "reach":
+            a[:, 2] = a[:, 2] - 0.4                      # bias downwards: plenty of gripper-table / gripper-object contact
+        env.step(a)
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(n, 256, replace=False))
+    worst = dict(q=0.0, ee=0.0, obj=0.0, rew=0)
+    compared = 0
+    for rep in range(3):
+        before = env.get_state().cpu().numpy()
+        a = torch.rand((n, A), device="cuda", generator=g) * 2 - 1
+        if task != "reach":
+            a[:, 2] = a[:, 2] - 0.4
+        obs, rew, term, trunc, _ = env.step(a)
+        after = env.get_state().cpu().numpy()
+        a_h, obs_h, rew_h, done_h = a.cpu().numpy(), obs["observation"].cpu().numpy(), rew.cpu().numpy(), (term | trunc).cpu().numpy().astype(bool)
+        for i in pick:
+            oe = OracleEnv(task, control)
+            oe.set_full_state(before[i, :-1])
+            ob, ag, dg, r, s = oe.step(a_h[i])
+            if not done_h[i]:                            # a finished env was reset in the same call: its rows hold the new episode
+                st = oe.full_state()
+                worst["q"] = max(worst["q"], np.abs(after[i, :9] - st[:9]).max())
+                worst["ee"] = max(worst["ee"], np.abs(obs_h[i, :3] - ob[:3]).max())
+                for o in range(nobj):
+                    worst["obj"] = max(worst["obj"], np.abs(after[i, 18 + 13 * o:25 + 13 * o] - st[18 + 13 * o:25 + 13 * o]).max())
+                compared += 1
+            thr = {"stack": 0.1, "flip": 0.2}.get(task, 0.05)
+            d_or = float(np.linalg.norm(ag.astype(np.float64) - dg.astype(np.float64)))
+            if abs(d_or - thr) > 1e-3:
+                worst["rew"] += int(float(rew_h[i]) != float(r))
+            oe.close()
+    print(f"{task}/{control} at {n} envs: {compared} env-steps compared with the oracle: {worst}")
+    assert compared > 600, compared
+    assert worst["q"] < 1e-4 and worst["ee"] < 1e-4 and worst["obj"] < 5e-4 and worst["rew"] == 0, worst
+    env.close()
