@@ -34,7 +34,9 @@ def _host(task, n=20000):
 
 
 def _same_dist(a, b):
-    return stats.ks_2samp(a, b).pvalue > 1e-3
+    # rounded to 1e-6: the device state is float32, so an atom of the distribution (PickAndPlace's 30 % goals at exactly z = 0.02)
+    # would otherwise sit an ulp away from the host's float64 atom and register as a 0.3 jump in the KS statistic
+    return stats.ks_2samp(np.round(a, 6), np.round(b, 6)).pvalue > 1e-3
 
 
 @pytest.mark.parametrize("task", ["reach", "push", "slide", "pick_and_place", "stack", "flip"])
