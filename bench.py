@@ -24,11 +24,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "env-steps/sec"
-# dram__bytes_read.sum + dram__bytes_write.sum per env-step call = per step_kernel launch (committed `ncu --set full` captures,
-# profiles/r1_step_kernel*_ncu_full_raw.csv; ncu flushes the caches before every replay pass, so these are cold-cache figures) x the
-# step_kernel launches one step is cut into; None where no capture exists for the configuration
-NCU_TRAFFIC = {("reach", "joints", 65536): 4 * 8396032, ("pick_and_place", "ee", 32768): 80 * 1758720}
-STEP_LAUNCHES = {("reach", "joints", 65536): "4 launches of 5 sub-steps (512 blocks)", ("pick_and_place", "ee", 32768): "4 env groups x 20 launches of 1 sub-step (64 blocks)"}
+# `roofline.traffic` / `launches_per_step` come from profiles/kernel_traffic.json, which scripts/ncu_traffic.py writes from an
+# `ncu --set full` capture of this very command (dram__bytes_read.sum + dram__bytes_write.sum of the step kernel, per launch; ncu
+# flushes the caches before every replay pass, so these are cold-cache figures) -- null where no capture exists for the configuration.
+PREROLL = 60          # untimed steps before any timed region: every env is past its first episode, contact states are mixed (steady state)
+
+
+def kernel_traffic(task, control, envs):
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        return d.get(f"{task}/{control}/{envs}")
+    except Exception:
+        return None
+
+
 ENV_IDS = {"reach": "PandaReach", "push": "PandaPush", "slide": "PandaSlide", "pick_and_place": "PandaPickAndPlace", "stack": "PandaStack", "flip": "PandaFlip"}
 TASK_ID = {"reach": 0, "push": 1, "slide": 2, "pick_and_place": 3, "stack": 4, "flip": 5}
 # algorithmic bytes per env-step, fp32 SoA: read state+goal+action, write state+obs+ag+dg+reward+2 flags
@@ -54,43 +63,56 @@ def workload_name(task, control, reward, envs):
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def oracle_lib():
     from tests.oracle_util import build_oracle
-    lib = ctypes.CDLL(build_oracle())
-    lib.po_bench_run.restype = ctypes.c_double
-    lib.po_bench_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong]
-    return lib
+    return ctypes.CDLL(build_oracle())
 
 
-def cpu_rollout(lib, task, control, steps_per_thread, threads, seed0=1):
-    """`threads` OS threads (ctypes releases the GIL), each stepping its own oracle env; returns env-steps/s."""
-    def work(i):
-        lib.po_bench_run(TASK_ID[task], 0 if control == "ee" else 1, steps_per_thread, seed0 + i)
-    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    dt = time.perf_counter() - t0
-    return threads * steps_per_thread / dt, dt
+class CpuPool:
+    """`threads` persistent OS threads (ctypes releases the GIL), each owning one persistent oracle env for the whole run."""
+
+    def __init__(self, lib, task, control, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.lib, self.threads = lib, threads
+        lib.po_bench_open.restype = ctypes.c_void_p
+        lib.po_bench_open.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong]
+        lib.po_bench_steps.restype = ctypes.c_double
+        lib.po_bench_steps.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.po_bench_close.argtypes = [ctypes.c_void_p]
+        self.handles = [lib.po_bench_open(TASK_ID[task], 0 if control == "ee" else 1, 1 + i) for i in range(threads)]
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.run(60)                                    # the same pre-roll as the GPU arm: envs past their first episode
+
+    def run(self, steps_per_thread):
+        """Every thread advances its env by steps_per_thread env-steps; returns (env-steps/s, seconds)."""
+        t0 = time.perf_counter()
+        list(self.pool.map(lambda h: self.lib.po_bench_steps(h, steps_per_thread), self.handles))
+        dt = time.perf_counter() - t0
+        return self.threads * steps_per_thread / dt, dt
+
+    def close(self):
+        self.pool.shutdown()
+        for h in self.handles:
+            self.lib.po_bench_close(h)
 
 
 def run_reference(args):
     """The reference's own CPU implementation of the path.  pybullet is not installable here, so this arm
-    times the oracle port (fp64 C restatement of the PyBullet path) on all host cores: kind = "port"."""
+    times the oracle port (fp64 C restatement of the PyBullet path, -O3) on all host cores: kind = "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     lib = oracle_lib()
-    rate, _ = cpu_rollout(lib, args.task, args.control, 50, cores)                      # calibration
+    pool = CpuPool(lib, args.task, args.control, cores)
+    rate, _ = pool.run(50)                                                               # calibration
     total = args.steps + args.warmup
-    per_thread = max(1, min(64, int(120.0 * rate / max(1, total) / cores)))             # bounded sample: whole run <= ~2 min
+    per_thread = max(1, min(256, int(120.0 * rate / max(1, total) / cores)))            # bounded sample: whole run <= ~2 min
     for _ in range(args.warmup):
-        cpu_rollout(lib, args.task, args.control, per_thread, cores)
+        pool.run(per_thread)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        cpu_rollout(lib, args.task, args.control, per_thread, cores, seed0=1000 * k + 1)
+        pool.run(per_thread)
     dt = time.perf_counter() - t0
+    pool.close()
     sample = cores * per_thread
     value = sample * args.steps / dt
     line = {
@@ -98,7 +120,7 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.task, args.control, args.reward, args.envs), "sample": f"{sample} env-steps per bench step"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} threads x {per_thread} env-steps per bench step, oracle/panda_oracle.c (PyBullet unavailable on this box)"},
+                         "sample": f"{cores} persistent threads x {per_thread} env-steps per bench step, oracle/panda_oracle.c -O3 (PyBullet unavailable on this box)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -151,11 +173,8 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n, A = args.envs, action_dim(args.task, args.control)
-    env = p.PandaVecEnv(args.task, n, reward_type=args.reward, control_type=args.control, device=local, seed=args.seed, env_id_offset=rank * n, auto_reset=True)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ncyc = 8
-    actions = torch.rand((ncyc, n, A), device=dev, generator=gen) * 2 - 1          # synthetic actions, resident in HBM
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                   # > 126 MB L2
 
     def barrier():
@@ -163,80 +182,86 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for w in range(args.warmup):
-        env.step(actions[w % ncyc])
-    barrier()
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_leg(task, control, n, steps, warmup):
+        """PREROLL + warmup untimed steps, then `steps` device-timed steps (CUDA events around each step on the launching stream, L2
+        flushed between them).  Returns (env, actions, device seconds on this rank, launches)."""
+        A = action_dim(task, control)
+        env = p.PandaVecEnv(task, n, reward_type=args.reward, control_type=control, device=local, seed=args.seed, env_id_offset=rank * n, auto_reset=True)
+        actions = torch.rand((ncyc, n, A), device=dev, generator=gen) * 2 - 1      # synthetic actions, resident in HBM
+        for w in range(PREROLL + warmup):
+            env.step(actions[w % ncyc])
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = p.kernel_launches()
+        for k, (a, b) in enumerate(ev):
+            flush.zero_()                              # L2 flush between timed iterations (outside the event pair)
+            a.record(); env.step(actions[(k + warmup) % ncyc]); b.record()
+        barrier()
+        return env, actions, sum(a.elapsed_time(b) for a, b in ev) / 1e3, p.kernel_launches() - l0
+
+    n, A = args.envs, action_dim(args.task, args.control)
     sampler = ClockSampler(local) if rank == 0 else None
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    launches0 = p.kernel_launches()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                                  # L2 flush between timed iterations (outside the event pair)
-        starts[k].record()
-        env.step(actions[(k + args.warmup) % ncyc])
-        ends[k].record()
-    barrier()
+    env, actions, dev_s_local, launches = timed_leg(args.task, args.control, n, args.steps, args.warmup)
     t_wall = time.perf_counter() - t_wall0
-    launches = p.kernel_launches() - launches0
     clocks = sampler.stop() if sampler else None
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    dev_s = sum(step_ms) / 1e3
-    t = torch.tensor([dev_s], dtype=torch.float64, device=dev)
+    dev_s = allmax(dev_s_local)                                                     # max over ranks
     stats = torch.tensor(env.stats(), dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)       # max over ranks
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)   # the only data-path-adjacent collective: episode statistics (4 doubles, NCCL)
-    dev_s = float(t.item())
     value = world * n * args.steps / dev_s
 
-    # end to end through the C ABI with host buffers (H2D + kernel + D2H per step)
+    # end to end through the C ABI with host buffers (per env group: H2D actions, kernels, D2H observations / rewards, pipelined)
     e2e_steps = max(3, min(args.steps, 50))
     host_actions = [env.pin_host(np.ascontiguousarray(actions[i].cpu().numpy())) for i in range(ncyc)]     # pinned host inputs (the e2e contract)
-    env.step_host(host_actions[0])
+    env.step_host(host_actions[0]); env.step_host(host_actions[1])
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         env.step_host(host_actions[k % ncyc])
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_local = time.perf_counter() - t0
+    e2e_s = allmax(e2e_local)
+    per_rank = torch.zeros(world, dtype=torch.float64, device=dev); per_rank[rank] = e2e_local
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(te.item())
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    e2e_value = world * n * e2e_steps / e2e_s
     h2d = n * A * 4
     d2h = n * (OBS[args.task] + 2 * GOAL[args.task] + 1) * 4 + 2 * n
+    diverged = env.diverged()
+    env.close(); del actions
 
-    # BASELINE.json's metric names two workloads: the default run (Reach joints, configs[1]) also reports PandaPickAndPlace-v3 at
-    # configs[3]'s per-GPU batch, timed the same way (informational: the headline `value` is the workload named in `config`)
+    # BASELINE.json's metric and configs name more workloads than the headline one: the default run also reports them, each at its
+    # BASELINE batch size per GPU and timed the same way (PREROLL, device events, L2 flush).  Informational: the headline `value`
+    # is the workload named in `config`.
     also = None
     if args.task == "reach" and args.control == "joints" and not args.no_her:
-        n2, k2, sec2, err2 = 32768, 40, -1.0, None
-        try:                          # rank-local work only inside the try: a failure on one rank must not leave the others in a collective
-            env2 = p.PandaVecEnv("pick_and_place", n2, reward_type=args.reward, control_type="ee", device=local, seed=args.seed, env_id_offset=rank * n2, auto_reset=True)
-            act2 = torch.rand((ncyc, n2, 4), device=dev, generator=gen) * 2 - 1
-            for w in range(10):
-                env2.step(act2[w % ncyc])
-            torch.cuda.synchronize(dev)
-            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k2)]
-            for k, (a, b) in enumerate(ev):
-                flush.zero_()
-                a.record(); env2.step(act2[k % ncyc]); b.record()
-            torch.cuda.synchronize(dev)
-            sec2 = sum(a.elapsed_time(b) for a, b in ev) / 1e3
-            env2.close(); del act2
-        except Exception as exc:
-            err2 = repr(exc)
-        t2 = torch.tensor([sec2, 1.0 if err2 is None else 0.0], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t2.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)       # slowest rank
-            tmin = t2.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)       # did every rank succeed?
-            t2 = torch.stack([tmax[0], tmin[1]])
-        if float(t2[1].item()) == 1.0 and float(t2[0].item()) > 0:
-            also = {"workload": workload_name("pick_and_place", "ee", args.reward, n2), "value": world * n2 * k2 / float(t2[0].item()), "unit": "env-steps/s",
-                    "ms_per_step": 1e3 * float(t2[0].item()) / k2, "steps": k2, "warmup": 10, "envs_per_gpu": n2}
-        else:
-            also = {"error": err2 or "failed on another rank"}
+        also = []
+        for task2, ctrl2, n2, k2 in (("reach", "ee", 65536, 30), ("pick_and_place", "ee", 32768, 30), ("push", "ee", 65536, 20), ("slide", "ee", 65536, 20), ("stack", "ee", 65536, 15)):
+            sec2, err2 = -1.0, None
+            try:                          # rank-local work only inside the try: a failure on one rank must not leave the others in a collective
+                env2, act2, sec2, _ = timed_leg(task2, ctrl2, n2, k2, 3)
+                env2.close(); del act2
+            except Exception as exc:
+                err2 = repr(exc)
+            t2 = torch.tensor([sec2, 1.0 if err2 is None else 0.0], dtype=torch.float64, device=dev)
+            if world > 1:
+                tmax = t2.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)       # slowest rank
+                tmin = t2.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)       # did every rank succeed?
+                t2 = torch.stack([tmax[0], tmin[1]])
+            if float(t2[1].item()) == 1.0 and float(t2[0].item()) > 0:
+                bps2 = bytes_per_step(task2, ctrl2)
+                also.append({"workload": workload_name(task2, ctrl2, args.reward, n2), "value": world * n2 * k2 / float(t2[0].item()), "unit": "env-steps/s",
+                             "ms_per_step": 1e3 * float(t2[0].item()) / k2, "steps": k2, "preroll": PREROLL, "envs_per_gpu": n2,
+                             "hbm_frac": bps2 * n2 * k2 / float(t2[0].item()) / 1e9 / 6541.8})
+            else:
+                also.append({"workload": workload_name(task2, ctrl2, args.reward, n2), "error": err2 or "failed on another rank"})
 
     # HER relabelling kernel (the one genuinely HBM-bound kernel of the path): compute_reward on M transitions
     her = None
@@ -269,8 +294,10 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
         ms = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
         nbytes = M * (16 + 3 * G * 4 + 4)
+        sector_bytes = M * (16 + 2 * 64 + G * 4 + 4)        # each 24-byte row gather touches two 32-byte sectors in the worst (and, unaligned, the typical) case
         her["her_relabel_1M_of_16M_rows_6d (gather + reward, includes the two output allocations)"] = {
             "transitions_per_s": M / (ms / 1e3), "ms": ms, "achieved_gbs": nbytes / (ms / 1e3) / 1e9, "bytes_per_transition": 16 + 3 * G * 4 + 4,
+            "achieved_gbs_in_sector_terms": sector_bytes / (ms / 1e3) / 1e9,
             "note": "row gathers of 24 B touch 32-64 B of DRAM sectors each: sector traffic, not algorithmic bytes, bounds this kernel"}
         del nag, dgb, src, gs
     if rank == 0:
@@ -283,21 +310,25 @@ def run_gpu(args):
         bps = bytes_per_step(args.task, args.control)
         kernel_s = dev_s / args.steps
         achieved = bps * n / kernel_s / 1e9
+        kt = kernel_traffic(args.task, args.control, n) or {}
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.task, args.control, args.reward, n), "envs_per_gpu": n, "sub_steps_per_step": 20,
-                       "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "parallelism": f"env-sharded x{world}, no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "pg_step_host (C ABI, host buffers)"},
+                       "preroll_steps": PREROLL, "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "pg_step_host (C ABI, host buffers)",
+                    "per_rank_s": [float(x) for x in per_rank.tolist()], "device_s_for_the_same_steps": dev_s * e2e_steps / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.task, args.control, n)),
-                         "kernel": "step_kernel", "launches_per_step": STEP_LAUNCHES.get((args.task, args.control, n)), "bytes_per_env_step": bps, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (kt.get("dram_bytes_per_launch") * kt.get("step_kernel_launches_per_step")) if kt else None,
+                         "kernel": "step_kernel", "launches_per_step": kt.get("launches_per_step") if kt else None, "traffic_source": kt.get("source") if kt else None,
+                         "bytes_per_env_step": bps, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "latency/issue-bound kernel (~1 MFLOP of serial dynamics per env-step): the HBM fraction is structurally tiny, see DESIGN.md"},
             "also": also,
             "her_compute_reward": her,
             "clocks": clocks,
-            "wall_s_timed_loop": t_wall,
-            "episode_stats": {"diverged_env_steps": env.diverged(), "episodes": stats[0].item(), "success_rate": (stats[1] / stats[0]).item() if stats[0].item() > 0 else None,
+            "wall_s_timed_leg": t_wall,
+            "episode_stats": {"diverged_env_steps": diverged, "episodes": stats[0].item(), "success_rate": (stats[1] / stats[0]).item() if stats[0].item() > 0 else None,
                               "mean_return": (stats[2] / stats[0]).item() if stats[0].item() > 0 else None},
         }
         if her:
@@ -306,13 +337,14 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             lib = oracle_lib()
-            rate, _ = cpu_rollout(lib, args.task, args.control, 25, cores)
+            pool = CpuPool(lib, args.task, args.control, cores)
+            rate, _ = pool.run(25)
             per_thread = max(25, int(12.0 * rate / cores))                      # ~12 s of CPU work
-            cpu_value, cpu_dt = cpu_rollout(lib, args.task, args.control, per_thread, cores)
+            cpu_value, cpu_dt = pool.run(per_thread)
+            pool.close()
             line["cpu_baseline"] = {"value": cpu_value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"{cores} threads x {per_thread} env-steps of the same workload ({cpu_dt:.1f} s), oracle/panda_oracle.c (PyBullet unavailable)"}
+                                    "sample": f"{cores} persistent threads x {per_thread} env-steps of the same workload ({cpu_dt:.1f} s), oracle/panda_oracle.c -O3 (PyBullet unavailable)"}
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -916,22 +916,34 @@ void po_env_get_full_state(PoEnv *e, double *st) {
 /* ------------------------------------------------------------------ CPU baseline driver (bench.py cpu_baseline / --impl reference)
  * Random-action rollout of one env, reset on success or at the TimeLimit (test/envs_test.py:6-14 loop), xorshift actions. */
 static double rnd01(unsigned long long *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return (double)(*s >> 11) / 9007199254740992.0; }
-double po_bench_run(int task, int control, int n_steps, unsigned long long seed) {
-    PoEnv *e = po_env_create(task, control, PO_REWARD_SPARSE);
-    unsigned long long st = seed * 2654435761ULL + 88172645463325252ULL;
-    float obs[32], ag[6], dg[6], rew, act[8]; unsigned char term = 0; double acc = 0; int t = 0, na = po_env_action_dim(e), limit = task == PO_STACK ? 100 : 50;
+typedef struct { PoEnv *e; unsigned long long st; int t, task; unsigned char term; } PoBench;
+static void bench_reset(PoBench *b) {
+    int task = b->task; unsigned long long *st = &b->st; float obs[32], ag[6], dg[6];
+    double goal[6] = {0.3 * rnd01(st) - 0.15, 0.3 * rnd01(st) - 0.15, task == PO_REACH ? 0.3 * rnd01(st) : 0.02, 0, 0, 0.06};
+    double op[6] = {0.3 * rnd01(st) - 0.15, 0.3 * rnd01(st) - 0.15, task == PO_SLIDE ? 0.03 : 0.02, 0.3 * rnd01(st) - 0.15, 0.3 * rnd01(st) - 0.15, 0.06};
+    if (task == PO_STACK) { goal[3] = goal[0]; goal[4] = goal[1]; }
+    if (task == PO_FLIP) { goal[0] = goal[1] = goal[2] = 0; goal[3] = 1; }
+    po_env_reset(b->e, goal, op, obs, ag, dg); b->t = 0; b->term = 0;
+}
+/* persistent form: one env kept across calls (bench.py's thread pool owns one per host thread) */
+void *po_bench_open(int task, int control, unsigned long long seed) {
+    PoBench *b = (PoBench *)calloc(1, sizeof(PoBench));
+    b->e = po_env_create(task, control, PO_REWARD_SPARSE); b->task = task; b->st = seed * 2654435761ULL + 88172645463325252ULL;
+    bench_reset(b);
+    return b;
+}
+double po_bench_steps(void *h, int n_steps) {
+    PoBench *b = (PoBench *)h; float obs[32], ag[6], dg[6], rew, act[8]; double acc = 0;
+    int na = po_env_action_dim(b->e), limit = b->task == PO_STACK ? 100 : 50;
     for (int i = 0; i < n_steps; i++) {
-        if (i == 0 || term || t >= limit) {
-            double goal[6] = {0.3 * rnd01(&st) - 0.15, 0.3 * rnd01(&st) - 0.15, task == PO_REACH ? 0.3 * rnd01(&st) : 0.02, 0, 0, 0.06};
-            double op[6] = {0.3 * rnd01(&st) - 0.15, 0.3 * rnd01(&st) - 0.15, task == PO_SLIDE ? 0.03 : 0.02, 0.3 * rnd01(&st) - 0.15, 0.3 * rnd01(&st) - 0.15, 0.06};
-            if (task == PO_STACK) { goal[3] = goal[0]; goal[4] = goal[1]; }
-            if (task == PO_FLIP) { goal[0] = goal[1] = goal[2] = 0; goal[3] = 1; }
-            po_env_reset(e, goal, op, obs, ag, dg); t = 0;
-        }
-        for (int k = 0; k < na; k++) act[k] = (float)(2 * rnd01(&st) - 1);
-        po_env_step(e, act, obs, ag, dg, &rew, &term); t++;
+        if (b->term || b->t >= limit) bench_reset(b);
+        for (int k = 0; k < na; k++) act[k] = (float)(2 * rnd01(&b->st) - 1);
+        po_env_step(b->e, act, obs, ag, dg, &rew, &b->term); b->t++;
         acc += obs[0] + rew;
     }
-    po_env_destroy(e);
     return acc;
+}
+void po_bench_close(void *h) { PoBench *b = (PoBench *)h; po_env_destroy(b->e); free(b); }
+double po_bench_run(int task, int control, int n_steps, unsigned long long seed) {
+    void *h = po_bench_open(task, control, seed); double acc = po_bench_steps(h, n_steps); po_bench_close(h); return acc;
 }

@@ -84,6 +84,9 @@ void po_env_step(PoEnv *e, const float *action, float *obs, float *ag, float *dg
 void po_env_step_batch(PoEnv **envs, int n, int na, int no, int ng, const float *actions, float *obs, float *ag, float *dg, float *reward, unsigned char *terminated);
 void po_env_set_full_state(PoEnv *e, const double *st);
 void po_env_get_full_state(PoEnv *e, double *st);
+void *po_bench_open(int task, int control, unsigned long long seed);
+double po_bench_steps(void *h, int n_steps);
+void po_bench_close(void *h);
 double po_bench_run(int task, int control, int n_steps, unsigned long long seed);
 
 /* ---- rewards (utils.py:4-30; tasks/ is_success / compute_reward) ---- */

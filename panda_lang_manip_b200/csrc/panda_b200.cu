@@ -296,11 +296,19 @@ int pg_set_substeps(pg_env* e, int n_substeps) {
     e->Ef.P.nsub = e->Ed.P.nsub = n_substeps;
     return PG_OK;
 }
-int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated,
-                     unsigned char* truncated, int auto_reset, void* stream) {
-    if (!e || !actions) return fail(PG_ERR_ARG, "pg_step: NULL handle or actions");
-    if (e->task == PG_TASK_BARE) return fail(PG_ERR_ARG, "pg_step: a bare world is advanced with pg_sim_step");
-    if (target_quat && e->ctrl != CTRL_EE) return fail(PG_ERR_ARG, "pg_step_oriented: a target orientation needs ee control");
+// Host-buffer mode of a step (pg_step_host): every env group copies its own action rows in before its first launch and its own
+// output rows out after its last one, on its own stream -- group g's device-to-host copies overlap group g+1's kernels.
+struct HostIO { const float* act; float* obs; float* ag; float* dg; float* rew; unsigned char* term; unsigned char* trunc; };
+static int ensure_group_streams(pg_env* e, int k) {
+    if (!e->ev_fork) PG_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    for (int g = 0; g < k; g++) {
+        if (!e->gstream[g]) PG_CUDA(cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking));
+        if (!e->ev_join[g]) PG_CUDA(cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming));
+    }
+    return PG_OK;
+}
+static int step_impl(pg_env* e, const float* actions, const float* target_quat, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated,
+                     unsigned char* truncated, int auto_reset, cudaStream_t stream, const HostIO* hio) {
     PG_CUDA(cudaSetDevice(e->device));
     // Contact-aware scheduling (see perm_*_kernel): large batches are re-sorted by their contact state before every launch, and a
     // step is cut into `segments` launches of consecutive sub-steps so that envs which make contact mid-step are regrouped; small
@@ -312,15 +320,19 @@ int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, 
     int* perm = e->precision == PG_F32 ? e->Ef.perm : e->Ed.perm;
     EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
     if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
-    const int groups = use_perm ? e->groups : 1;
+    int groups = use_perm ? e->groups : 1;
+    if (hio && use_perm && e->n >= 16384 && groups < 4) groups = 4;     // host mode: at least 4 groups to pipeline the copies against
+    if (groups > 1) { int rc = ensure_group_streams(e, groups); if (rc != PG_OK) return rc; }
     // group g owns the envs (and thread slots) [g * gsize, min(n, (g + 1) * gsize)), gsize a multiple of the sort chunk
     const int gsize = ((e->n + groups - 1) / groups + PERM_CHUNK - 1) / PERM_CHUNK * PERM_CHUNK;
-    if (groups > 1) PG_CUDA(cudaEventRecord(e->ev_fork, (cudaStream_t)stream));
+    const size_t A = e->act_dim, O = e->obs_dim, G = e->goal_dim;
+    if (groups > 1) PG_CUDA(cudaEventRecord(e->ev_fork, stream));
     for (int g = 0; g < groups; g++) {
         const int t0 = g * gsize, cnt = std::min(e->n, t0 + gsize) - t0;
         if (cnt <= 0) break;
-        cudaStream_t st = groups > 1 ? e->gstream[g] : (cudaStream_t)stream;
+        cudaStream_t st = groups > 1 ? e->gstream[g] : stream;
         if (groups > 1) PG_CUDA(cudaStreamWaitEvent(st, e->ev_fork, 0));
+        if (hio) PG_CUDA(cudaMemcpyAsync(const_cast<float*>(actions) + t0 * A, hio->act + t0 * A, (size_t)cnt * A * sizeof(float), cudaMemcpyHostToDevice, st));
         Ef.t0 = Ed.t0 = t0; Ef.tcount = Ed.tcount = cnt;
         const int nchunks = (cnt + PERM_CHUNK - 1) / PERM_CHUNK;
         int* ghist = hist + (size_t)(t0 / PERM_CHUNK + g) * PERM_BUCKETS;
@@ -335,10 +347,25 @@ int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, 
             }
             if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, st); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, st);
         }
-        if (groups > 1) { PG_CUDA(cudaEventRecord(e->ev_join[g], st)); PG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_join[g], 0)); }
+        if (hio) {
+            if (hio->obs) PG_CUDA(cudaMemcpyAsync(hio->obs + t0 * O, obs + t0 * O, (size_t)cnt * O * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (hio->ag) PG_CUDA(cudaMemcpyAsync(hio->ag + t0 * G, ag + t0 * G, (size_t)cnt * G * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (hio->dg) PG_CUDA(cudaMemcpyAsync(hio->dg + t0 * G, dg + t0 * G, (size_t)cnt * G * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (hio->rew) PG_CUDA(cudaMemcpyAsync(hio->rew + t0, reward + t0, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (hio->term) PG_CUDA(cudaMemcpyAsync(hio->term + t0, terminated + t0, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+            if (hio->trunc) PG_CUDA(cudaMemcpyAsync(hio->trunc + t0, truncated + t0, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        }
+        if (groups > 1) { PG_CUDA(cudaEventRecord(e->ev_join[g], st)); PG_CUDA(cudaStreamWaitEvent(stream, e->ev_join[g], 0)); }
     }
     PG_CUDA(cudaGetLastError());
     return PG_OK;
+}
+int pg_step_oriented(pg_env* e, const float* actions, const float* target_quat, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated,
+                     unsigned char* truncated, int auto_reset, void* stream) {
+    if (!e || !actions) return fail(PG_ERR_ARG, "pg_step: NULL handle or actions");
+    if (e->task == PG_TASK_BARE) return fail(PG_ERR_ARG, "pg_step: a bare world is advanced with pg_sim_step");
+    if (target_quat && e->ctrl != CTRL_EE) return fail(PG_ERR_ARG, "pg_step_oriented: a target orientation needs ee control");
+    return step_impl(e, actions, target_quat, obs, ag, dg, reward, terminated, truncated, auto_reset, (cudaStream_t)stream, nullptr);
 }
 
 static int ensure_host_path(pg_env* e) {
@@ -374,27 +401,27 @@ int pg_host_unpin(void* ptr) {
 
 int pg_step_host(pg_env* e, const float* actions, float* obs, float* ag, float* dg, float* reward, unsigned char* terminated, unsigned char* truncated, int auto_reset) {
     if (!e || !actions) return fail(PG_ERR_ARG, "pg_step_host: NULL handle or actions");
+    if (e->task == PG_TASK_BARE) return fail(PG_ERR_ARG, "pg_step_host: a bare world is advanced with pg_sim_step");
     PG_CUDA(cudaSetDevice(e->device));
     int rc = ensure_host_path(e); if (rc != PG_OK) return rc;
     const size_t n = (size_t)e->n, O = e->obs_dim, G = e->goal_dim;
     // pageable buffers go through the handle's pinned staging slabs (one extra host copy each way); pinned ones are copied directly
     const float* src = actions;
     if (!host_pinned(actions)) { memcpy(e->h_act, actions, n * e->act_dim * sizeof(float)); src = e->h_act; }
-    PG_CUDA(cudaMemcpyAsync(e->d_act, src, n * e->act_dim * sizeof(float), cudaMemcpyHostToDevice, e->hstream));
     float* d_obs = e->d_out; float* d_ag = d_obs + n * O; float* d_dg = d_ag + n * G; float* d_rew = d_dg + n * G;
     unsigned char* d_term = (unsigned char*)(d_rew + n); unsigned char* d_trunc = d_term + n;
-    rc = pg_step(e, e->d_act, d_obs, d_ag, d_dg, d_rew, d_term, d_trunc, auto_reset, e->hstream); if (rc != PG_OK) return rc;
-    struct Out { void* user; const void* dev; size_t off, bytes; bool direct; };
-    Out outs[6] = {{obs, d_obs, 0, n * O * sizeof(float), false}, {ag, d_ag, 0, n * G * sizeof(float), false}, {dg, d_dg, 0, n * G * sizeof(float), false},
-                   {reward, d_rew, 0, n * sizeof(float), false}, {terminated, d_term, 0, n, false}, {truncated, d_trunc, 0, n, false}};
+    struct Out { void* user; const void* dev; void* host; size_t bytes; bool direct; };
+    Out outs[6] = {{obs, d_obs, nullptr, n * O * sizeof(float), false}, {ag, d_ag, nullptr, n * G * sizeof(float), false}, {dg, d_dg, nullptr, n * G * sizeof(float), false},
+                   {reward, d_rew, nullptr, n * sizeof(float), false}, {terminated, d_term, nullptr, n, false}, {truncated, d_trunc, nullptr, n, false}};
     for (Out& o : outs) {
-        o.off = (size_t)((const char*)o.dev - (const char*)e->d_out);
         if (!o.user) continue;
         o.direct = host_pinned(o.user);
-        PG_CUDA(cudaMemcpyAsync(o.direct ? o.user : (void*)((char*)e->h_out + o.off), o.dev, o.bytes, cudaMemcpyDeviceToHost, e->hstream));
+        o.host = o.direct ? o.user : (void*)((char*)e->h_out + ((const char*)o.dev - (const char*)e->d_out));
     }
+    HostIO hio{src, (float*)outs[0].host, (float*)outs[1].host, (float*)outs[2].host, (float*)outs[3].host, (unsigned char*)outs[4].host, (unsigned char*)outs[5].host};
+    rc = step_impl(e, e->d_act, nullptr, d_obs, d_ag, d_dg, d_rew, d_term, d_trunc, auto_reset, e->hstream, &hio); if (rc != PG_OK) return rc;
     PG_CUDA(cudaStreamSynchronize(e->hstream));
-    for (const Out& o : outs) if (o.user && !o.direct) memcpy(o.user, (const char*)e->h_out + o.off, o.bytes);
+    for (const Out& o : outs) if (o.user && !o.direct) memcpy(o.user, o.host, o.bytes);
     return PG_OK;
 }
 
