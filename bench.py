@@ -194,6 +194,11 @@ def run_gpu(args):
         A = action_dim(task, control)
         env = p.PandaVecEnv(task, n, reward_type=args.reward, control_type=control, device=local, seed=args.seed, env_id_offset=rank * n, auto_reset=True)
         actions = torch.rand((ncyc, n, A), device=dev, generator=gen) * 2 - 1      # synthetic actions, resident in HBM
+        # steady state: spread the episode phases (all envs are created at step 0 and would otherwise walk through their episodes in
+        # lock-step: contact-free early steps, TimeLimit resets in bursts) by giving every env a random age, then pre-roll
+        st = env.get_state()
+        st[:, -1] = torch.randint(0, env.max_episode_steps, (n,), device=dev, generator=gen).to(st.dtype)
+        env.set_state(st); del st
         for w in range(PREROLL + warmup):
             env.step(actions[w % ncyc])
         barrier()

@@ -321,7 +321,9 @@ static int step_impl(pg_env* e, const float* actions, const float* target_quat, 
     EnvDev<float> Ef = e->Ef; EnvDev<double> Ed = e->Ed;
     if (!use_perm) { Ef.perm = nullptr; Ed.perm = nullptr; }
     int groups = use_perm ? e->groups : 1;
-    if (hio && use_perm && e->n >= 16384 && groups < 4) groups = 4;     // host mode: at least 4 groups to pipeline the copies against
+    // host mode pipelines the copies against the env groups the configuration already has; PG_HOST_GROUPS forces more (measured: on one
+    // GPU the single-stream Reach-joints configuration loses 5 % when cut into 4 groups only to overlap 0.2 ms of copies)
+    if (hio && use_perm && e->n >= 16384) { static const int hg = getenv("PG_HOST_GROUPS") ? atoi(getenv("PG_HOST_GROUPS")) : 0; if (hg > groups && hg <= 8) groups = hg; }
     if (groups > 1) { int rc = ensure_group_streams(e, groups); if (rc != PG_OK) return rc; }
     // group g owns the envs (and thread slots) [g * gsize, min(n, (g + 1) * gsize)), gsize a multiple of the sort chunk
     const int gsize = ((e->n + groups - 1) / groups + PERM_CHUNK - 1) / PERM_CHUNK * PERM_CHUNK;

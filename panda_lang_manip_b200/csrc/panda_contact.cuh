@@ -470,9 +470,9 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
     bool live = false;
     int it = 0;
     for (; it < 50; it++) {
-        T res = T(0);
-        joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, live);
-        if (FAST && live) break;
+        T res = T(0), watch = T(0);
+        joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, watch);
+        if (FAST && watch > T(0)) { live = true; break; }
         if (nc > 0) {
             T d8[8], F8[8];
 #pragma unroll
@@ -513,7 +513,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     C.f(c, C_APP) = app + di;
                     contact_apply<T, NOBJ>(S, W, Op, X, X.n * di, d8, F8, dvl, dva, ob);
                 }
-                T r = div_fast(di, inv); res = fmax(res, r * r);
+                res = fmax(res, fabs(div_fast(di, inv)));
             };
             auto friction_rows = [&](int c, auto kind) {          // implicit friction cone over the two tangent rows
                 constexpr int K = decltype(kind)::value;
@@ -565,8 +565,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
                     contact_apply<T, NOBJ>(S, W, Op, X, t1 * d1 + t2 * d2, d8, F8, dvl, dva, ob);
                 }
-                T r1 = div_fast(d1, i1), r2 = div_fast(d2, i2);
-                res = fmax(res, fmax(r1 * r1, r2 * r2));
+                res = fmax(res, fmax(fabs(div_fast(d1, i1)), fabs(div_fast(d2, i2))));
             };
             {
                 int c = 0;
@@ -600,7 +599,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
 #ifdef PG_HOST_DEBUG
         g_dbg_sweeps++;
 #endif
-        if (res <= T(1e-7)) break;
+        if (res * res <= T(1e-7)) break;
     }
 #ifdef PG_HOST_DEBUG
     g_dbg_solves++; g_dbg_contacts += nc;

@@ -628,7 +628,7 @@ template <int D, int FIRST, typename T> PG_HD void limit_pair(const T (*Minv)[ND
         const T wi = sg * di;
         dv[D] += Minv[D][D] * wi;
         w += wi;
-        T r = di * Minv[D][D]; res = fmax(res, r * r);
+        res = fmax(res, fabs(di * Minv[D][D]));
     }
 #pragma unroll
     for (int k = 0; k < ND; k++) if (k != D) dv[k] += Minv[k][D] * w;
@@ -639,19 +639,20 @@ template <int D, typename T> PG_HD void motor_row(const Model<T>& M, const T (*M
     R.mot_app[D] = app + di;
 #pragma unroll
     for (int k = 0; k < ND; k++) dv[k] += Minv[k][D] * di;
-    T r = di * Minv[D][D]; res = fmax(res, r * r);
+    res = fmax(res, fabs(di * Minv[D][D]));
 }
 // An arm limit row that rests at zero impulse and whose update would stay clamped at zero is an exact no-op, and that is the
 // state of the 14 arm limit rows in almost every sweep.  The FAST sweep therefore only *watches* them (same expression as the
 // real row, 3 instructions instead of 29) and raises `live` if one would have engaged; the caller then redoes the solve with
 // the full sweep.  Finger limit rows (the blocked gripper sits on its lower limit, an open one on the upper) stay real rows.
-template <int D, int SIDE, typename T> PG_HD void limit_watch(const JointRows<T>& R, const T* dv, bool& live) {
+// `watch` accumulates the largest "accumulated impulse this row would reach" over the watched rows of a sweep (their applied impulse is
+// exactly 0 while they are only watched, so it is just rhs - J dv / D); the sweep's caller tests watch > 0 once.
+template <int D, int SIDE, typename T> PG_HD void limit_watch(const JointRows<T>& R, const T* dv, T& watch) {
     const T sg = SIDE == 0 ? T(1) : T(-1);
-    T sum = R.lim_app[2 * D + SIDE] + (R.lim_rhs[2 * D + SIDE] - sg * dv[D] * R.invD[D]);
-    live = live || (sum > T(0));
+    watch = fmax(watch, R.lim_rhs[2 * D + SIDE] - sg * dv[D] * R.invD[D]);
 }
 template <int D, bool FAST, typename T> struct RowsFwd {
-    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, bool& live) {
+    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, T& live) {
         RowsFwd<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
         if (FAST && D < 7) { limit_watch<D, 0>(R, dv, live); limit_watch<D, 1>(R, dv, live); }
         else limit_pair<D, 0>(Mi, R, dv, res);
@@ -659,11 +660,11 @@ template <int D, bool FAST, typename T> struct RowsFwd {
     static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, FAST, T>::mot(M, Mi, R, dv, res); motor_row<D>(M, Mi, R, dv, res); }
 };
 template <bool FAST, typename T> struct RowsFwd<-1, FAST, T> {
-    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, bool&) {}
+    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, T&) {}
     static PG_HD void mot(const Model<T>&, const T (*)[ND], JointRows<T>&, T*, T&) {}
 };
 template <int D, bool FAST, typename T> struct RowsRev {
-    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, bool& live) {
+    static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, T& live) {
         if (FAST && D < 7) { limit_watch<D, 1>(R, dv, live); limit_watch<D, 0>(R, dv, live); }
         else limit_pair<D, 1>(Mi, R, dv, res);
         RowsRev<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
@@ -671,11 +672,13 @@ template <int D, bool FAST, typename T> struct RowsRev {
     static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { motor_row<D>(M, Mi, R, dv, res); RowsRev<D - 1, FAST, T>::mot(M, Mi, R, dv, res); }
 };
 template <bool FAST, typename T> struct RowsRev<-1, FAST, T> {
-    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, bool&) {}
+    static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, T&) {}
     static PG_HD void mot(const Model<T>&, const T (*)[ND], JointRows<T>&, T*, T&) {}
 };
-// one sweep over the non-contact rows; Bullet alternates the direction with the iteration parity
-template <bool FAST, typename T> PG_HD void joint_rows_sweep(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, int it, T& res, bool& live) {
+// one sweep over the non-contact rows; Bullet alternates the direction with the iteration parity.  `res` accumulates the largest
+// |velocity change| of the sweep (the exit test squares it: max of squares == square of the max magnitude, rounding is monotone);
+// `watch` > 0 afterwards means a watched arm-limit row would have engaged.
+template <bool FAST, typename T> PG_HD void joint_rows_sweep(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, int it, T& res, T& live) {
     if (it & 1) { RowsFwd<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); RowsFwd<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); }
     else { RowsRev<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); RowsRev<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); }
 }
@@ -701,10 +704,9 @@ template <typename T> PG_HD void robot_substep(const Model<T>& M, T* q, T* qd, c
 #pragma unroll
     for (int d = 0; d < ND; d++) dv[d] = T(0);
     for (int it = 0; it < 50; it++) {
-        T res = T(0);
-        bool live = false;
-        joint_rows_sweep<false>(M, Minv, R, dv, it, res, live);
-        if (res <= T(1e-7)) break;
+        T res = T(0), watch = T(0);
+        joint_rows_sweep<false>(M, Minv, R, dv, it, res, watch);
+        if (res * res <= T(1e-7)) break;
     }
 #pragma unroll
     for (int d = 0; d < ND; d++) { qd[d] += dv[d]; q[d] += qd[d] * Consts<T>::dt; }
