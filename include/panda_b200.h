@@ -166,6 +166,17 @@ int pg_get_link_state(pg_env* env, int link, double* out, void* stream);
  * get_ee_orientation, panda_gym/envs/robots/panda_cartesian.py:218-225). */
 int pg_get_ee_pose(pg_env* env, double* pose, void* stream);
 
+/* The fork's camera path, PyBullet.render (panda_gym/pybullet.py:149-264) with the camera of get_cam2world_transforms (:70-107), for
+ * every env of the handle: camera = {target x, y, z, distance, yaw, pitch, roll} (HOST, degrees; the reference's defaults are
+ * {0,0,0, 1.4, 45, -30, 0}), fov 60, near 0.1, far 100.  Analytic ray casting of the primitives the kernels simulate (plane, table,
+ * free bodies, the robot as its physics boxes -- its visual meshes are not in the reference tree).  DEVICE outputs, each may be NULL:
+ * depth [N,H,W] float32 = OpenGL depth-buffer values as getCameraImage returns them (1.0 = nothing hit); rgba [N,H,W,4] uint8 (flat
+ * body colours of the task scenes, diffuse shading); segmentation [N,H,W] uint8 (0 background, 1 plane, 2 table, 3/4 objects,
+ * 5 robot base, 6 + link); points [N,H,W,3] float32 = the reference's deprojection of every pixel through inv(P V) (NaN where
+ * filtered) with valid [N,H,W] uint8: depth buffer < 0.99 and, with crop != 0, the workspace box 0 < z < 0.67, -0.5 < x < 0.2. */
+int pg_render(pg_env* env, int width, int height, const double* camera, int crop, float* depth, unsigned char* rgba,
+              unsigned char* segmentation, float* points, unsigned char* valid, void* stream);
+
 /* Episode statistics accumulated by auto-reset since creation: {episodes, successes, return_sum, length_sum} (host). */
 int pg_stats(pg_env* env, double out[4]);
 /* Number of env-steps that ended in a non-finite state (counted; with auto_reset the env is truncated and restarted). */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "pg_compute_reward_host", "pg_is_success_host", "pg_her_relabel", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_get_ee_pose", "pg_create_bare", "pg_set_motors", "pg_get_motors", "pg_sim_step", "pg_inverse_kinematics_link", "pg_get_link_state",
     "pg_save_state_async", "pg_restore_state_async", "pg_host_stage_allocations", "pg_reset_seeded", "pg_set_task_params", "pg_set_substeps",
-    "pg_compute_reward_t", "pg_is_success_t", "pg_her_relabel_t", "pg_compute_reward_host_t", "pg_is_success_host_t", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
+    "pg_render", "pg_compute_reward_t", "pg_is_success_t", "pg_her_relabel_t", "pg_compute_reward_host_t", "pg_is_success_host_t", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
 _lib = None
@@ -82,6 +82,7 @@ def load() -> ctypes.CDLL:
     lib.pg_reset_seeded.argtypes = [vp] * 9
     lib.pg_set_task_params.argtypes = [vp, cd, vp, vp, vp, vp]
     lib.pg_set_substeps.argtypes = [vp, c_int]
+    lib.pg_render.argtypes = [vp, c_int, c_int, vp, c_int, vp, vp, vp, vp, vp, vp]
     lib.pg_compute_reward_t.argtypes = [c_int, c_int, cd, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_is_success_t.argtypes = [c_int, cd, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_her_relabel_t.argtypes = [c_int, c_int, cd, vp, vp, vp, vp, vp, vp, vp, c_ll, c_int, vp]

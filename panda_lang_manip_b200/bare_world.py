@@ -115,6 +115,11 @@ class PandaBareWorld:
         torch.cuda.current_stream(self.device).synchronize()
         return out
 
+    def render(self, *args, **kwargs):
+        """As PandaVecEnv.render: depth / colour / point cloud of every world (pg_render)."""
+        from .vec_env import PandaVecEnv
+        return PandaVecEnv.render(self, *args, **kwargs)
+
     def save_state(self) -> int:
         import ctypes
         sid = ctypes.c_int()

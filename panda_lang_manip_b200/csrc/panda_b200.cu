@@ -12,6 +12,7 @@
 #include "panda_kernels.cuh"
 #include "panda_model.h"
 #include "panda_scene.h"
+#include "panda_render.h"
 
 namespace pg {
 long long g_launches = 0;
@@ -22,6 +23,8 @@ static int cuda_fail(cudaError_t e, const char* what) { return fail(PG_ERR_CUDA,
 
 template <typename T, int TASK> cudaError_t configure_step(void);       // panda_step_task.cu
 template <typename T> cudaError_t configure_bare(void);                 // panda_bare.cu
+template <typename T> void launch_render_setup(const EnvDev<T>& E, const RenderScene& R, RenderPrim* prims, cudaStream_t st);   // panda_render.cu
+void launch_render(const RenderPrim* prims, const RenderCamera& C, int n_envs, float* depth, unsigned char* rgba, unsigned char* seg, float* points, unsigned char* valid, cudaStream_t st);
 #define PG_DECL(T, K)                                                                                        \
     extern template void launch_step<T, K>(const EnvDev<T>&, int, const StepIO&, cudaStream_t);              \
     extern template void launch_reset<T, K>(const EnvDev<T>&, const ResetIO&, cudaStream_t);                 \
@@ -62,6 +65,7 @@ struct pg_env {
     void* blob = nullptr; size_t blob_bytes = 0;      // one allocation: q, qd, obj, goal, steps, episode, ret, stats
     EnvDev<float> Ef; EnvDev<double> Ed;
     std::map<int, void*> snaps; int next_snap = 0;
+    RenderPrim* prims = nullptr; RenderScene rscene;  // analytic renderer: per-env primitive lists (allocated at the first pg_render)
     std::vector<void*> snap_pool;                    // buffers of removed snapshots, reused by the next save (no allocation in a save / remove loop)
     bool sort_envs = true;                            // PG_SORT_ENVS=0 disables the contact-aware thread->env map (A/B measurements)
     // env groups: sorted batches are cut into groups of consecutive envs, each advanced on its own stream, so that the tail of
@@ -243,6 +247,7 @@ int pg_destroy(pg_env* e) {
     for (int g = 0; g < 8; g++) { if (e->gstream[g]) cudaStreamDestroy(e->gstream[g]); if (e->ev_join[g]) cudaEventDestroy(e->ev_join[g]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->dbg) cudaFree(e->dbg);
+    if (e->prims) cudaFree(e->prims);
     cudaFree(e->blob);
     delete e;
     return PG_OK;
@@ -643,6 +648,58 @@ int pg_sim_step(pg_env* e, int n_substeps, void* stream) {
     PG_CUDA(cudaSetDevice(e->device));
     if (e->precision == PG_F32) launch_bare_step<float>(e->Ef, e->nobj, n_substeps, (cudaStream_t)stream);
     else launch_bare_step<double>(e->Ed, e->nobj, n_substeps, (cudaStream_t)stream);
+    PG_CUDA(cudaGetLastError());
+    return PG_OK;
+}
+static void fill_render_scene(pg_env* e) {
+    RenderScene& R = e->rscene;
+    memset(&R, 0, sizeof R);
+    const Scene<double>& S = e->precision == PG_F32 ? scene_cast<double>(e->Ef.S) : e->Ed.S;
+    R.nobj = e->nobj;
+    R.has_table = S.table_x0 < S.table_x1; R.table[0] = (float)S.table_x0; R.table[1] = (float)S.table_x1; R.table[2] = (float)S.table_y0; R.table[3] = (float)S.table_y1; R.table_height = 0.4f;
+    R.has_plane = S.ground_z > -1e29; R.plane_z = (float)S.ground_z;
+    const double bz = e->precision == PG_F32 ? (double)e->Ef.M.base[2] : e->Ed.M.base[2];
+    R.has_robot = bz < 500.0;                                  // a bare world without a robot parks it 1 km up
+    const float bc[3] = {-0.04f, 0.0f, 0.07f}, bh[3] = {0.11f, 0.1f, 0.07f};     // panda_link0: approximate extents (its mesh is not available)
+    for (int k = 0; k < 3; k++) { R.base_c[k] = bc[k]; R.base_h[k] = bh[k]; }
+    for (int l = 0; l < 7; l++) for (int k = 0; k < 3; k++) { R.link_c[l][k] = (float)kLinks[l].com[k]; R.link_h[l][k] = (float)(0.5 * kLinks[l].box[k]); }
+    const int rb_link[3] = {8, 9, 10};
+    for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) { R.link_c[rb_link[b]][k] = (float)S.rb_c[b][k]; R.link_h[rb_link[b]][k] = (float)S.rb_h[b][k]; }
+}
+int pg_render(pg_env* e, int width, int height, const double* camera, int crop, float* depth, unsigned char* rgba, unsigned char* segmentation, float* points,
+              unsigned char* valid, void* stream) {
+    if (!e || !camera || width <= 0 || height <= 0 || width > 4096 || height > 4096) return fail(PG_ERR_ARG, "pg_render: bad argument");
+    if (valid && !points) return fail(PG_ERR_ARG, "pg_render: valid is the point cloud's mask, it needs points");
+    PG_CUDA(cudaSetDevice(e->device));
+    if (!e->prims) { PG_CUDA(cudaMalloc(&e->prims, (size_t)e->n * RENDER_MAX_PRIMS * sizeof(RenderPrim))); fill_render_scene(e); }
+    // b3ComputeViewMatrixFromYawPitchRoll (up axis 2) + computeProjectionMatrixFOV(fov 60, near 0.1, far 100): pybullet.py:90-102
+    const double rad = 0.01745329251994329547, yaw = camera[4] * rad, pitch = camera[5] * rad, roll = camera[6] * rad, dist = camera[3];
+    const double cy = cos(yaw), sy = sin(yaw), cr = cos(roll), sr = sin(roll), cp = cos(pitch), sp = sin(pitch);
+    // eyeRot.setEulerZYX(yaw, roll, pitch): R = Rz(yaw) Ry(roll) Rx(pitch)
+    const double Rm[3][3] = {{cy * cr, cy * sr * sp - sy * cp, cy * sr * cp + sy * sp}, {sy * cr, sy * sr * sp + cy * cp, sy * sr * cp - cy * sp}, {-sr, cr * sp, cr * cp}};
+    double eye[3], up[3], f[3], sv[3], u[3];
+    for (int k = 0; k < 3; k++) { eye[k] = Rm[k][1] * -dist + camera[k]; up[k] = Rm[k][2]; f[k] = camera[k] - eye[k]; }
+    double fl = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    if (!(fl > 0)) return fail(PG_ERR_ARG, "pg_render: camera distance must be > 0");
+    for (int k = 0; k < 3; k++) f[k] /= fl;
+    sv[0] = f[1] * up[2] - f[2] * up[1]; sv[1] = f[2] * up[0] - f[0] * up[2]; sv[2] = f[0] * up[1] - f[1] * up[0];
+    double sl = sqrt(sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2]);
+    for (int k = 0; k < 3; k++) sv[k] /= sl;
+    u[0] = sv[1] * f[2] - sv[2] * f[1]; u[1] = sv[2] * f[0] - sv[0] * f[2]; u[2] = sv[0] * f[1] - sv[1] * f[0];
+    RenderCamera C; memset(&C, 0, sizeof C);
+    C.width = width; C.height = height; C.crop = crop;
+    for (int k = 0; k < 3; k++) { C.eye[k] = (float)eye[k]; C.fwd[k] = (float)f[k]; C.right[k] = (float)sv[k]; C.up[k] = (float)u[k]; }
+    C.tan_half_fov = (float)tan(30.0 * rad); C.aspect = (float)width / (float)height; C.near = 0.1f; C.far = 100.0f;
+    const double l[3] = {0.35, -0.25, 0.9}; const double ll = sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    for (int k = 0; k < 3; k++) C.light[k] = (float)(l[k] / ll);
+    const unsigned char col[RENDER_ID_ROBOT + 1][4] = {{0, 0, 0, 255}, {38, 38, 38, 255}, {242, 242, 242, 255},
+                                                      {(unsigned char)(e->task == PG_TASK_STACK ? 26 : (e->task == PG_TASK_FLIP ? 255 : 26)), (unsigned char)(e->task == PG_TASK_STACK ? 26 : (e->task == PG_TASK_FLIP ? 255 : 230)),
+                                                       (unsigned char)(e->task == PG_TASK_STACK ? 230 : (e->task == PG_TASK_FLIP ? 255 : 26)), 255},
+                                                      {26, 230, 26, 255}, {235, 235, 235, 255}};     // plane 0.15, table 0.95, objects (tasks/ *.py rgba_color), robot
+    memcpy(C.color, col, sizeof col);
+    C.background[0] = 223; C.background[1] = 54; C.background[2] = 45; C.background[3] = 255;          // pybullet.py:28 default background_color
+    if (e->precision == PG_F32) launch_render_setup<float>(e->Ef, e->rscene, e->prims, (cudaStream_t)stream); else launch_render_setup<double>(e->Ed, e->rscene, e->prims, (cudaStream_t)stream);
+    launch_render(e->prims, C, e->n, depth, rgba, segmentation, points, valid, (cudaStream_t)stream);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
 }

@@ -27,7 +27,7 @@ class PyBullet:
 
     def __init__(self, render: bool = False, n_substeps: int = 20, background_color: Optional[np.ndarray] = None) -> None:
         if render:
-            raise NotImplementedError("the B200 backend has no on-screen renderer (reference pybullet.py:34 GUI mode); see PyBullet.render for depth / point clouds")
+            raise NotImplementedError("the B200 backend has no on-screen GUI (reference pybullet.py:34 p.GUI); PyBullet.render gives depth / colour / point clouds off-screen")
         if int(n_substeps) < 1:
             raise ValueError("n_substeps must be >= 1")
         self.n_substeps = int(n_substeps)
@@ -315,10 +315,68 @@ class PyBullet:
     def no_rendering(self) -> Iterator[None]:
         yield
 
-    def render(self, *args, **kwargs):
-        raise NotImplementedError("no renderer on the B200 backend")
+    def get_cam2world_transforms(self, width: int = 480, height: int = 480, target_position=None, distance: float = 1.4, yaw: float = 45, pitch: float = -30, roll: float = 0):
+        """reference pybullet.py:70-107: (view_matrix, proj_matrix) as pybullet's 16-tuples (column-major) and inv(P V).  Host matrix
+        algebra on 4x4s, as in the reference (computeViewMatrixFromYawPitchRoll, up axis 2; computeProjectionMatrixFOV 60 deg, 0.1, 100)."""
+        t = np.zeros(3) if target_position is None else np.asarray(target_position, dtype=np.float64)
+        V, P = view_matrix(t, distance, yaw, pitch, roll), projection_matrix(60.0, float(width) / height, 0.1, 100.0)
+        return tuple(V.reshape(-1, order="F")), tuple(P.reshape(-1, order="F")), np.linalg.inv(P @ V)
+
+    def deproject(self, depth, pixels, tran_pix_world, width: int = 480, height: int = 480):
+        """reference pybullet.py:109-147: pixel coordinates (x, y) + depth-buffer image -> world points."""
+        pixels = np.asarray(pixels)
+        x = pixels[:, 0] * 1 / width * 2 - 1
+        y = (height - pixels[:, 1]) * 1 / height * 2 - 1
+        z = 2 * np.asarray(depth)[pixels[:, 1], pixels[:, 0]] - 1
+        pts = (tran_pix_world @ np.stack([x, y, z, np.ones_like(z)], axis=1).T).T
+        return (pts / pts[:, 3:4])[:, :3]
+
+    def render(self, width: int = 480, height: int = 480, target_position=None, distance: float = 1.4, yaw: float = 45, pitch: float = -30, roll: float = 0, waypoints=None):
+        """reference pybullet.py:149-264: (rgb, depth, points, colors, pixels_2d, waypoints_proj).  The image is ray-cast on the device
+        (pg_render; the robot is drawn as its physics boxes, its meshes are not part of the reference tree); the compaction of the
+        valid pixels into the point list is host-side boolean indexing, in the reference's row-major pixel order."""
+        t = np.zeros(3) if target_position is None else np.asarray(target_position, dtype=np.float64)
+        r = self._backend().render(width, height, t, distance, yaw, pitch, roll, crop=True, rgb=True, points=True)
+        rgb, depth = r["rgb"][0].cpu().numpy(), r["depth"][0].cpu().numpy()
+        valid = r["valid"][0].cpu().numpy().reshape(-1)
+        points = r["points"][0].cpu().numpy().reshape(-1, 3)[valid].astype(np.float64)
+        colors = rgb.reshape(-1, 3)[valid]
+        rows, cols = np.divmod(np.nonzero(valid)[0], width)
+        pixels_2d = np.stack([cols.astype(np.float64), rows.astype(np.float64)], axis=1)      # (x, y) of each kept pixel, y measured from the top
+        waypoints_proj = []
+        if waypoints is not None:
+            PV = projection_matrix(60.0, float(width) / height, 0.1, 100.0) @ view_matrix(t, distance, yaw, pitch, roll)
+            for p in waypoints:
+                x, y, z, w = PV @ np.array([p[0], p[1], p[2], 1.0])
+                waypoints_proj.append([int((x / w + 1) / 2 * width), int(height - (y / w + 1) / 2 * height)])
+        return rgb, depth, points, colors, pixels_2d, waypoints_proj
 
     _reset_obs = None
+
+
+def view_matrix(target, distance, yaw, pitch, roll) -> np.ndarray:
+    """pybullet computeViewMatrixFromYawPitchRoll(upAxisIndex=2) as a 4x4 (row-major maths): the eye sits at R (0, -distance, 0) + target with
+    R = Rz(yaw) Ry(roll) Rx(pitch), looking at the target, up = R e_z."""
+    y, p, r = np.radians([yaw, pitch, roll])
+    Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+    Ry = np.array([[np.cos(r), 0, np.sin(r)], [0, 1, 0], [-np.sin(r), 0, np.cos(r)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(p), -np.sin(p)], [0, np.sin(p), np.cos(p)]])
+    R = Rz @ Ry @ Rx
+    target = np.asarray(target, dtype=np.float64)
+    eye, up = R @ np.array([0.0, -distance, 0.0]) + target, R @ np.array([0.0, 0.0, 1.0])
+    f = (target - eye) / np.linalg.norm(target - eye)
+    s = np.cross(f, up); s /= np.linalg.norm(s)
+    u = np.cross(s, f)
+    V = np.eye(4)
+    V[0, :3], V[1, :3], V[2, :3] = s, u, -f
+    V[:3, 3] = -V[:3, :3] @ eye
+    return V
+
+
+def projection_matrix(fov, aspect, near, far) -> np.ndarray:
+    """pybullet computeProjectionMatrixFOV (the OpenGL perspective matrix)."""
+    ys = 1.0 / np.tan(np.radians(fov) / 2)
+    return np.array([[ys / aspect, 0, 0, 0], [0, ys, 0, 0], [0, 0, (near + far) / (near - far), 2 * near * far / (near - far)], [0, 0, -1, 0]])
 
 
 def _dof(joint: int) -> int:

@@ -242,6 +242,28 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_get_ee_pose(self._h, _ptr(out), self._stream()))
         return out
 
+    def render(self, width: int = 480, height: int = 480, target_position=(0.0, 0.0, 0.0), distance: float = 1.4, yaw: float = 45, pitch: float = -30, roll: float = 0,
+               crop: bool = True, rgb: bool = True, points: bool = True, segmentation: bool = False) -> Dict[str, torch.Tensor]:
+        """PyBullet.render (the fork's camera path, pybullet.py:149-264) for every env: analytic ray casting of the primitive scene.
+        Returns a dict of device tensors: ``depth`` [N,H,W] (OpenGL depth-buffer values), ``rgb`` [N,H,W,3] uint8, ``points`` [N,H,W,3]
+        (the reference's deprojection; NaN where filtered) with ``valid`` [N,H,W] bool (depth < 0.99 and, with ``crop``, the
+        reference's workspace box), ``segmentation`` [N,H,W] uint8."""
+        n, dev = self.num_envs, self.device
+        cam = np.ascontiguousarray([*[float(x) for x in target_position], float(distance), float(yaw), float(pitch), float(roll)], dtype=np.float64)
+        out = {"depth": torch.empty((n, height, width), dtype=torch.float32, device=dev)}
+        rgba = torch.empty((n, height, width, 4), dtype=torch.uint8, device=dev) if rgb else None
+        pts = torch.empty((n, height, width, 3), dtype=torch.float32, device=dev) if points else None
+        val = torch.empty((n, height, width), dtype=torch.uint8, device=dev) if points else None
+        seg = torch.empty((n, height, width), dtype=torch.uint8, device=dev) if segmentation else None
+        _lib.check(self.lib.pg_render(self._h, int(width), int(height), cam.ctypes.data, int(bool(crop)), _ptr(out["depth"]), _ptr(rgba), _ptr(seg), _ptr(pts), _ptr(val), self._stream()))
+        if rgb:
+            out["rgb"] = rgba[..., :3]
+        if points:
+            out["points"], out["valid"] = pts, val.bool()
+        if segmentation:
+            out["segmentation"] = seg
+        return out
+
     def diverged(self) -> int:
         """Env-steps that ended in a non-finite state since creation (0 in a healthy run)."""
         import ctypes

@@ -5,7 +5,8 @@ import panda_lang_manip_b200 as p
 task, ctrl, n = sys.argv[1], sys.argv[2], int(sys.argv[3])
 env = p.PandaVecEnv(task, n, control_type=ctrl)
 g = torch.Generator(device='cuda'); g.manual_seed(0)
-for t in range(17):
+st = env.get_state(); st[:, -1] = torch.randint(0, env.max_episode_steps, (n,), device='cuda', generator=g).to(st.dtype); env.set_state(st)     # steady state: random episode phases
+for t in range(int(sys.argv[4]) if len(sys.argv) > 4 else 70):
     a = torch.rand((n, env.action_dim), device='cuda', generator=g) * 2 - 1
     env.step(a)
 torch.cuda.synchronize()
