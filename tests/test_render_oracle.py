@@ -20,8 +20,8 @@ def test_closed_form_deprojection_is_the_reference_arithmetic():
     ref = ro.deproject_reference(d, 96, 80, distance=1.0, yaw=30, pitch=-40)
     assert np.allclose(pts[valid], ref[valid], atol=1e-9)
     # hit points of the table top lie on z = 0 up to the reference's half-pixel bias (it deprojects pixel corners, the image samples centres)
-    top = valid & (seg == 2) & (pts[..., 2] > -0.03)                         # the table's top face (its sides are visible too)
-    assert top.sum() > 500 and np.abs(pts[top][:, 2]).max() < 0.02
+    top = valid & (seg == 2) & (pts[..., 2] > -0.012)                        # the table's top face (its sides are visible too, below it)
+    assert top.sum() > 1500 and np.abs(pts[top][:, 2]).max() < 0.012         # 96 x 80 pixels at 1 m: half a pixel is ~1 cm on the slanted table
     assert (seg == 3).sum() > 10                                             # the cube is visible
 
 
