@@ -125,6 +125,12 @@ int pg_her_relabel(int task, int reward_type, const void* next_achieved_goal, co
 int pg_her_relabel_t(int task, int reward_type, double threshold, const void* next_achieved_goal, const void* desired_goal,
                      const long long* src, const long long* goal_src, void* desired_goal_out, void* achieved_goal_out, float* reward,
                      long long m, int dtype, void* stream);
+/* The same with a row pitch (elements) for the two replay-buffer goal arrays: a buffer that stores its goals padded to 32 bytes
+ * (pitch 8 for fp32 goals of 3, 4 or 6 components) makes every gathered row exactly one DRAM sector instead of one or two.  Outputs
+ * stay dense [M, G].  pitch >= G. */
+int pg_her_relabel_pitched(int task, int reward_type, double threshold, const void* next_achieved_goal, const void* desired_goal,
+                           long long pitch, const long long* src, const long long* goal_src, void* desired_goal_out,
+                           void* achieved_goal_out, float* reward, long long m, int dtype, void* stream);
 /* Task.compute_reward / is_success on HOST arrays (what RobotTaskEnv.compute_reward, core.py:226, is called with by a CPU learner). */
 int pg_compute_reward_host(int task, int reward_type, const void* achieved_goal, const void* desired_goal, float* reward,
                            long long m, int dtype, int device);
@@ -181,6 +187,9 @@ int pg_render(pg_env* env, int width, int height, const double* camera, int crop
 int pg_stats(pg_env* env, double out[4]);
 /* Number of env-steps that ended in a non-finite state (counted; with auto_reset the env is truncated and restarted). */
 int pg_diverged(pg_env* env, long long* count);
+/* Number of contact candidates dropped because an env already held the per-sub-step cap (10 contacts for scenes with at most one
+ * object, 22 for Stack -- the size of the on-chip contact store; PyBullet has no such cap, the oracle applies the same one). */
+int pg_contact_overflows(pg_env* env, long long* count);
 /* Scheduling introspection (host buffers): the per-env 16-bit key written by the last launch and the thread -> env map built from
  * the previous one (bits 0-4 contacts at the end of the launch, bit 5 robot contact, bit 6 solver ran all sweeps, bit 7 near a
  * contact, bit 9 full joint-limit sweep, bits 10-13 generic contacts (Stack)). */

@@ -822,19 +822,19 @@ void po_is_success_f64(int task, const double *ag, const double *dg, unsigned ch
 }
 
 /* ------------------------------------------------------------------ env (core.py:229-289, panda.py, tasks/) */
-struct PoEnv { PoSim *sim; int task, control, reward, block_gripper, nsub; double goal[6]; float thr32; };
+struct PoEnv { PoSim *sim; int task, control, reward, block_gripper, nsub; double goal[6]; double thr; };
 static const double NEUTRAL[ND] = {0.00, 0.41, 0.00, -1.85, 0.00, 2.26, 0.79, 0.00, 0.00};
 static const double FORCES[ND] = {87.0, 87.0, 87.0, 87.0, 12.0, 120.0, 120.0, 170.0, 170.0};
 PoEnv *po_env_create(int task, int control, int reward) {
     PoEnv *e = (PoEnv *)calloc(1, sizeof(PoEnv));
     e->sim = po_create(task, -0.6, 0.0, 0.0); e->task = task; e->control = control; e->reward = reward;
     e->block_gripper = (task == PO_REACH || task == PO_PUSH || task == PO_SLIDE); /* panda_tasks.py:60,77,94 */
-    e->nsub = 20; e->thr32 = thr_f32(task);
+    e->nsub = 20; e->thr = thr_f64(task);
     return e;
 }
 void po_env_destroy(PoEnv *e) { po_destroy(e->sim); free(e); }
 /* PyBullet(n_substeps) (pybullet.py:26) and the task's distance_threshold (tasks/reach.py:15 ...) */
-void po_env_set_params(PoEnv *e, int n_substeps, double distance_threshold) { e->nsub = n_substeps; e->thr32 = (float)distance_threshold; }
+void po_env_set_params(PoEnv *e, int n_substeps, double distance_threshold) { e->nsub = n_substeps; e->thr = distance_threshold; }
 PoSim *po_env_sim(PoEnv *e) { return e->sim; }
 int po_env_goal_dim(const PoEnv *e) { return goal_dim(e->task); }
 int po_env_action_dim(const PoEnv *e) { return (e->control == PO_CTRL_EE ? 3 : 7) + (e->block_gripper ? 0 : 1); }
@@ -892,7 +892,9 @@ void po_env_step_oriented(PoEnv *e, const float *action, const double *target_qu
     for (int d = 0; d < ND; d++) po_control_joint(s, DOF_LINK[d], target[d], FORCES[d]);
     po_step(s, e->nsub);
     env_obs(e, obs, ag, dg);
-    { float d = dist_f32(e->task, ag, dg); *terminated = d < e->thr32; *reward = e->reward == PO_REWARD_SPARSE ? -(d > e->thr32 ? 1.0f : 0.0f) : -d; }
+    /* core.py:285-288: is_success / compute_reward on (float32 achieved goal, float64 task goal) -> numpy promotes to float64 */
+    { double a64[6]; for (int k = 0; k < goal_dim(e->task); k++) a64[k] = (double)ag[k];
+      double d = dist_f64(e->task, a64, e->goal); *terminated = d < e->thr; *reward = e->reward == PO_REWARD_SPARSE ? -(d > e->thr ? 1.0f : 0.0f) : -(float)d; }
 }
 
 /* batched forms for the test-suite's threaded / multi-process drivers: envs[i] steps with actions[i] */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "pg_compute_reward_host", "pg_is_success_host", "pg_her_relabel", "pg_save_state", "pg_restore_state", "pg_remove_state", "pg_get_state", "pg_set_state",
     "pg_inverse_kinematics", "pg_get_ee_pose", "pg_create_bare", "pg_set_motors", "pg_get_motors", "pg_sim_step", "pg_inverse_kinematics_link", "pg_get_link_state",
     "pg_save_state_async", "pg_restore_state_async", "pg_host_stage_allocations", "pg_reset_seeded", "pg_set_task_params", "pg_set_substeps",
-    "pg_render", "pg_compute_reward_t", "pg_is_success_t", "pg_her_relabel_t", "pg_compute_reward_host_t", "pg_is_success_host_t", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_stats", "pg_kernel_launches", "pg_last_error",
+    "pg_render", "pg_compute_reward_t", "pg_is_success_t", "pg_her_relabel_t", "pg_her_relabel_pitched", "pg_compute_reward_host_t", "pg_is_success_host_t", "pg_debug_schedule", "pg_debug_timing", "pg_diverged", "pg_contact_overflows", "pg_stats", "pg_kernel_launches", "pg_last_error",
 ]
 
 _lib = None
@@ -86,11 +86,13 @@ def load() -> ctypes.CDLL:
     lib.pg_compute_reward_t.argtypes = [c_int, c_int, cd, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_is_success_t.argtypes = [c_int, cd, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_her_relabel_t.argtypes = [c_int, c_int, cd, vp, vp, vp, vp, vp, vp, vp, c_ll, c_int, vp]
+    lib.pg_her_relabel_pitched.argtypes = [c_int, c_int, cd, vp, vp, c_ll, vp, vp, vp, vp, vp, c_ll, c_int, vp]
     lib.pg_compute_reward_host_t.argtypes = [c_int, c_int, cd, vp, vp, vp, c_ll, c_int, c_int]
     lib.pg_is_success_host_t.argtypes = [c_int, cd, vp, vp, vp, c_ll, c_int, c_int]
     lib.pg_debug_schedule.argtypes = [vp, vp, vp]
     lib.pg_debug_timing.argtypes = [vp, vp]
     lib.pg_diverged.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+    lib.pg_contact_overflows.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     lib.pg_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.pg_kernel_launches.restype = c_ll
     lib.pg_last_error.restype = ctypes.c_char_p

@@ -86,7 +86,7 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.stats = (double*)take(8 * sizeof(double));
     E.q = (T*)take(9 * n * sizeof(T)); E.qd = (T*)take(9 * n * sizeof(T));
     E.obj = (T*)take((size_t)(e->nobj > 0 ? e->nobj : 1) * 13 * n * sizeof(T));
-    E.goal = (T*)take(6 * n * sizeof(T));
+    E.goal = (double*)take(6 * n * sizeof(double));
     E.target = (T*)take(9 * n * sizeof(T));
     E.motor = (T*)take((e->task == PG_TASK_BARE ? 36 : 0) * n * sizeof(T));
     E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
@@ -107,15 +107,33 @@ template <typename E, bool WANT_REWARD> static void launch_reward(int task, cons
     g_launches++;
 }
 
-template <typename E> static void launch_her(int task, const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
-                                             long long m, int reward_type, double thr, cudaStream_t st) {
-    const int grid = (int)std::min<long long>((m + 255) / 256, 148LL * 16);
-    switch (task) {     // goal layouts: 3-D position (thr 0.05), Stack 6-D (thr 0.1), Flip quaternion (thr 0.2)
-    case 4: her_relabel_kernel<E, 4><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, reward_type, thr); break;
-    case 5: her_relabel_kernel<E, 5><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, reward_type, thr); break;
-    default: her_relabel_kernel<E, 0><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, reward_type, thr); break;
+// widest load (bytes) every row start allows: base pointers and the row pitch must both be multiples of it; a load that reaches past
+// the row's G elements (16-byte loads on 6-D fp32 rows) needs the padding to exist, i.e. pitch >= the loaded span
+template <typename E> static int her_vector_bytes(int G, const void* a, const void* b, long long pitch) {
+    const uintptr_t bits = (uintptr_t)a | (uintptr_t)b | (uintptr_t)(pitch * (long long)sizeof(E));
+    for (int vb = 16; vb > (int)sizeof(E); vb >>= 1) {
+        const int ev = vb / (int)sizeof(E), span = (G + ev - 1) / ev * ev;
+        if ((bits & (uintptr_t)(vb - 1)) == 0 && span <= pitch) return vb;
     }
+    return (int)sizeof(E);
+}
+template <typename E, int TASK> static void launch_her_task(const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
+                                                            long long m, long long pitch, int reward_type, double thr, cudaStream_t st) {
+    const long long per_block = 256LL * HER_INFLIGHT;
+    const int grid = (int)std::min<long long>((m + per_block - 1) / per_block, 148LL * 16);
+    const int vb = her_vector_bytes<E>(task_goal_dim(TASK), next_ag, dg, pitch);
+    if (vb == 16) her_relabel_kernel<E, TASK, 16><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
+    else if (vb == 8) her_relabel_kernel<E, TASK, 8><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
+    else her_relabel_kernel<E, TASK, (int)sizeof(E)><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
     g_launches++;
+}
+template <typename E> static void launch_her(int task, const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
+                                             long long m, long long pitch, int reward_type, double thr, cudaStream_t st) {
+    switch (task) {     // goal layouts: 3-D position (thr 0.05), Stack 6-D (thr 0.1), Flip quaternion (thr 0.2)
+    case 4: launch_her_task<E, 4>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    case 5: launch_her_task<E, 5>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    default: launch_her_task<E, 0>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    }
 }
 
 extern "C" {
@@ -454,15 +472,20 @@ int pg_compute_reward(int task, int reward_type, const void* ag, const void* dg,
 int pg_is_success(int task, const void* ag, const void* dg, unsigned char* success, long long m, int dtype, void* stream) {
     return pg_is_success_t(task, task >= 0 && task <= 5 ? threshold_f64(task) : 0.0, ag, dg, success, m, dtype, stream);
 }
-int pg_her_relabel_t(int task, int reward_type, double threshold, const void* next_ag, const void* dg, const long long* src, const long long* goal_src, void* dg_out, void* ag_out,
-                     float* reward, long long m, int dtype, void* stream) {
+int pg_her_relabel_pitched(int task, int reward_type, double threshold, const void* next_ag, const void* dg, long long pitch, const long long* src, const long long* goal_src,
+                           void* dg_out, void* ag_out, float* reward, long long m, int dtype, void* stream) {
     if (m == 0) return PG_OK;
     if (task < 0 || task > 5 || reward_type < 0 || reward_type > 1 || !next_ag || !dg || !src || !goal_src || !dg_out || !reward || m < 0 || !(threshold >= 0))
         return fail(PG_ERR_ARG, "pg_her_relabel: bad argument");
-    if (dtype == PG_F32) launch_her<float>(task, (const float*)next_ag, (const float*)dg, src, goal_src, (float*)dg_out, (float*)ag_out, reward, m, reward_type, threshold, (cudaStream_t)stream);
-    else launch_her<double>(task, (const double*)next_ag, (const double*)dg, src, goal_src, (double*)dg_out, (double*)ag_out, reward, m, reward_type, threshold, (cudaStream_t)stream);
+    if (pitch < task_goal_dim(task)) return fail(PG_ERR_ARG, "pg_her_relabel_pitched: the row pitch is smaller than the goal dimension");
+    if (dtype == PG_F32) launch_her<float>(task, (const float*)next_ag, (const float*)dg, src, goal_src, (float*)dg_out, (float*)ag_out, reward, m, pitch, reward_type, threshold, (cudaStream_t)stream);
+    else launch_her<double>(task, (const double*)next_ag, (const double*)dg, src, goal_src, (double*)dg_out, (double*)ag_out, reward, m, pitch, reward_type, threshold, (cudaStream_t)stream);
     PG_CUDA(cudaGetLastError());
     return PG_OK;
+}
+int pg_her_relabel_t(int task, int reward_type, double threshold, const void* next_ag, const void* dg, const long long* src, const long long* goal_src, void* dg_out, void* ag_out,
+                     float* reward, long long m, int dtype, void* stream) {
+    return pg_her_relabel_pitched(task, reward_type, threshold, next_ag, dg, task >= 0 && task <= 5 ? task_goal_dim(task) : 0, src, goal_src, dg_out, ag_out, reward, m, dtype, stream);
 }
 int pg_her_relabel(int task, int reward_type, const void* next_ag, const void* dg, const long long* src, const long long* goal_src, void* dg_out, void* ag_out,
                    float* reward, long long m, int dtype, void* stream) {
@@ -726,6 +749,14 @@ int pg_debug_timing(pg_env* e, long long* out) {
     PG_CUDA(cudaSetDevice(e->device));
     PG_CUDA(cudaDeviceSynchronize());
     PG_CUDA(cudaMemcpy(out, e->dbg, (size_t)e->n * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return PG_OK;
+}
+int pg_contact_overflows(pg_env* e, long long* count) {
+    if (!e || !count) return fail(PG_ERR_ARG, "pg_contact_overflows: NULL argument");
+    PG_CUDA(cudaSetDevice(e->device));
+    double d = 0;
+    PG_CUDA(cudaMemcpy(&d, (e->precision == PG_F32 ? e->Ef.stats : e->Ed.stats) + 5, sizeof(double), cudaMemcpyDeviceToHost));
+    *count = (long long)d;
     return PG_OK;
 }
 int pg_diverged(pg_env* e, long long* count) {

@@ -112,7 +112,7 @@ template <typename T> PG_HD void euler_from_quat(T x, T y, T z, T w, T* e) {
 
 // _get_obs: robot obs (ee pos, ee vel[, finger width]) ++ task obs; achieved goal; desired goal
 template <typename T, int TASK>
-PG_HD void env_observe(const Model<T>& M, const T* q, const T* qd, const T* qc, const Obj<T>* ob, const T* goal, float* obs, float* ag, float* dg) {
+PG_HD void env_observe(const Model<T>& M, const T* q, const T* qd, const T* qc, const Obj<T>* ob, const double* goal, float* obs, float* ag, float* dg) {
     constexpr int NOBJ = task_nobj(TASK);
     V3<T> p, v; ee_observe(M, q, qd, qc, p, v);
     int n = 0;
@@ -178,15 +178,27 @@ PG_HD void env_set_action(const Model<T>& M, const T* q, const T* qd, const floa
 // (two-object scenes only: measured +6 % on Stack, -5 % on the one-object scenes, whose batches fragment over the extra buckets).
 enum { KEY_ROBOT = 0x20, KEY_CAPPED = 0x40, KEY_NEAR = 0x80, KEY_FULL = 0x200 };
 
-// RobotTaskEnv.step for one environment, or the sub-step range [s0, s1) of it (a step may be cut into segments so that the envs can
-// be re-sorted in between; the motor targets travel through `target`).  q/qd/ob are updated in place; the observation, goals,
-// reward and success are produced by the segment that ends the step (s1 == 20).
+// RobotTaskEnv.step (core.py:280-289) evaluates is_success / compute_reward on (float32 achieved goal, FLOAT64 task goal): numpy promotes
+// the difference to float64, so the in-step distance, its comparison with the threshold and the dense reward's cast -d.astype(float32)
+// are float64 arithmetic on the float32-rounded achieved goal -- unlike compute_reward on two float32 arrays (the HER path, reward_kernel).
+// The goal is therefore stored in float64 whatever the simulation precision.
+template <int TASK>
+PG_HD void step_reward(int reward_type, const float* ag, const double* goal, double thr, float& reward, unsigned char& success) {
+    double a[task_goal_dim(TASK)];
+#pragma unroll
+    for (int k = 0; k < task_goal_dim(TASK); k++) a[k] = (double)ag[k];
+    const double d = goal_distance(TASK, a, goal);
+    success = d < thr;
+    reward = reward_from_distance(reward_type, d, thr);
+}
+
+// The simulation part of RobotTaskEnv.step for one environment, or the sub-step range [s0, s1) of it (a step may be cut into segments so
+// that the envs can be re-sorted in between; the motor targets travel through `target`).  q/qd/ob are updated in place; qc receives the
+// link-transform cache of the last sub-step (valid when s1 == nsub).
 template <typename T, int TASK, int CTRL>
-PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const T* goal, const float* action, const float* target_quat,
-                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& sched_key, T* target, int s0 = 0, int s1 = 20,
-                    int nsub = 20, float thr = -1.0f) {
+PG_HD void env_step_sim(const Model<T>& M, const Scene<T>& S, T* q, T* qd, Obj<T>* ob, const float* action, const float* target_quat, Contacts<T>& C, int& sched_key,
+                        T* target, T* qc, int s0 = 0, int s1 = 20, int nsub = 20) {
     constexpr int NOBJ = task_nobj(TASK);
-    T qc[ND];
     if (s0 == 0) env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
     // sticky: once an arm limit engaged, later sub-steps (and, through the key's KEY_FULL bit, the next segment / step) start with the
     // full sweep; it is dropped again after a segment in which no arm limit row carried impulse
@@ -197,21 +209,30 @@ PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q,
 #pragma unroll
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
-        // watched arm-limit rows: a measured policy -- +25 % with joint control, -13 % with ee control (contact rows dominate there and the
-        // fast instantiation schedules worse), so it is enabled for joint control only
-        env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
+        // watched arm-limit rows for both control types: the fallback is the rolled full sweep (joint_rows_sweep_rolled), so the kernel holds
+        // one solver loop and one copy of the contact code (round 1 carried a second unrolled instantiation, which cost ee control 13 %)
+        env_substep<T, NOBJ, true>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
         if (C.n > 0) nsub_contact++;
         near = near || C.near;
     }
     // scheduling key for the next launch (see perm_bucket): the contact picture of this launch's last sub-step
     const int ngen = C.n - C.nB - C.nA;                     // generic contacts (robot box <-> object, object <-> object): the most expensive rows
     sched_key = (C.n < 31 ? C.n : 31) | (NOBJ == 2 ? (ngen < 15 ? ngen : 15) << 10 : 0) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (limits_active ? KEY_FULL : 0);
-    if (s1 < nsub) return;
+}
+// _get_obs + is_success + compute_reward of the step that just ended (core.py:283-288)
+template <typename T, int TASK>
+PG_HD void env_step_finish(const Model<T>& M, int reward_type, const T* q, const T* qd, const T* qc, const Obj<T>* ob, const double* goal, double thr,
+                           float* obs, float* ag, float* dg, float& reward, unsigned char& success) {
     env_observe<T, TASK>(M, q, qd, qc, ob, goal, obs, ag, dg);
-    if (thr < 0.0f) thr = threshold_f32(TASK);
-    float d = goal_distance(TASK, ag, dg);
-    success = d < thr;
-    reward = reward_from_distance(reward_type, d, thr);
+    step_reward<TASK>(reward_type, ag, goal, thr, reward, success);
+}
+// the whole step (host test build and small callers)
+template <typename T, int TASK, int CTRL>
+PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const double* goal, const float* action, const float* target_quat,
+                    float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& sched_key, T* target, int nsub = 20, double thr = -1.0) {
+    T qc[ND];
+    env_step_sim<T, TASK, CTRL>(M, S, q, qd, ob, action, target_quat, C, sched_key, target, qc, 0, nsub, nsub);
+    env_step_finish<T, TASK>(M, reward_type, q, qd, qc, ob, goal, thr < 0.0 ? threshold_f64(TASK) : thr, obs, ag, dg, reward, success);
 }
 
 }  // namespace pg

@@ -19,13 +19,13 @@ template <typename T> struct EnvDev {
     T* q;                        // [9][n]
     T* qd;                       // [9][n]
     T* obj;                      // [nobj][13][n]  pos3 quat4 lin3 ang3
-    T* goal;                     // [6][n]
+    double* goal;                // [6][n] task goal, float64 whatever the simulation precision (core.py:285-288 evaluates success / reward against the float64 goal)
     T* target;                   // [9][n] motor targets of the step in flight (only live between the segments of a cut step); bare worlds: the motors' target angles
     T* motor;                    // bare worlds only: [4][9][n] position gain, velocity gain, target velocity, max impulse per sub-step (setJointMotorControlArray state)
     int* steps;                  // [n] steps since reset (TimeLimit)
     unsigned* episode;           // [n] episodes started (RNG counter)
     float* ret;                  // [n] running episode return
-    double* stats;               // [5] episodes, successes, return sum, length sum, diverged envs
+    double* stats;               // [6] episodes, successes, return sum, length sum, diverged envs, contact candidates dropped at the cap
     int* perm;                   // [n] thread -> env map of the next launch (contact-heavy envs first), or NULL
     int t0, tcount;              // sorted path: this launch covers the thread slots [t0, t0 + tcount) of perm (one env group)
     unsigned short* ccount;      // [n] scheduling key written by the env's last launch (see KEY_* in panda_env.cuh)
@@ -115,7 +115,7 @@ template <int W, typename E, int BS = BLOCK> __device__ __forceinline__ void til
 }
 
 // ---------------------------------------------------------------------------------------------- SoA state access
-template <typename T, int NOBJ> __device__ __forceinline__ void load_state(const EnvDev<T>& E, int i, T* q, T* qd, Obj<T>* ob, T* goal) {
+template <typename T, int NOBJ> __device__ __forceinline__ void load_state(const EnvDev<T>& E, int i, T* q, T* qd, Obj<T>* ob) {
     const int n = E.n;
 #pragma unroll
     for (int d = 0; d < ND; d++) { q[d] = E.q[d * n + i]; qd[d] = E.qd[d * n + i]; }
@@ -125,8 +125,10 @@ template <typename T, int NOBJ> __device__ __forceinline__ void load_state(const
         ob[o].pos = mk<T>(p[0], p[n], p[2 * n]); ob[o].qx = p[3 * n]; ob[o].qy = p[4 * n]; ob[o].qz = p[5 * n]; ob[o].qw = p[6 * n];
         ob[o].lin = mk<T>(p[7 * n], p[8 * n], p[9 * n]); ob[o].ang = mk<T>(p[10 * n], p[11 * n], p[12 * n]);
     }
+}
+template <typename T> __device__ __forceinline__ void load_goal(const EnvDev<T>& E, int i, double* goal) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) goal[k] = E.goal[k * n + i];
+    for (int k = 0; k < 6; k++) goal[k] = E.goal[k * E.n + i];
 }
 template <typename T, int NOBJ> __device__ __forceinline__ void store_state(const EnvDev<T>& E, int i, const T* q, const T* qd, const Obj<T>* ob) {
     const int n = E.n;
@@ -145,7 +147,7 @@ template <typename T, int NOBJ> __device__ __forceinline__ void store_state(cons
 // Distributions: reach.py:22-23,51-54; push.py:69-87; slide.py:23-24,73-91; pick_and_place.py:65-85; stack.py:94-119;
 // flip.py:63-80 (goal: uniform rotation, drawn from the device stream instead of scipy's unseeded global RNG).
 template <typename T, int TASK>
-__device__ __forceinline__ void env_reset(const EnvDev<T>& E, int i, uint32_t episode, const double* goal_ov, const double* obj_ov, T* q, T* qd, Obj<T>* ob, T* goal,
+__device__ __forceinline__ void env_reset(const EnvDev<T>& E, int i, uint32_t episode, const double* goal_ov, const double* obj_ov, T* q, T* qd, Obj<T>* ob, double* goal,
                                           const unsigned long long* seeds = nullptr) {
     constexpr int NOBJ = task_nobj(TASK);
     constexpr int G = task_goal_dim(TASK);
@@ -180,7 +182,7 @@ __device__ __forceinline__ void env_reset(const EnvDev<T>& E, int i, uint32_t ep
         for (int k = 0; k < 3 * NOBJ; k++) op[k] = obj_ov[(size_t)i * 3 * NOBJ + k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) goal[k] = (T)g[k];
+    for (int k = 0; k < 6; k++) goal[k] = g[k];
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) {
         ob[o].pos = mk<T>((T)op[3 * o], (T)op[3 * o + 1], (T)op[3 * o + 2]); ob[o].qx = T(0); ob[o].qy = T(0); ob[o].qz = T(0); ob[o].qw = T(1);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
     const bool mine = valid && (io.mask == nullptr || io.mask[i] != 0);
     float obs[O], ag[G], dg[G];
     if (mine) {
-        T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+        T q[ND], qd[ND]; double goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         uint32_t ep = E.episode[i] + 1u;
         env_reset<T, TASK>(E, i, ep, io.goal_override, io.object_override, q, qd, ob, goal, io.seeds);
         store_state<T, NOBJ>(E, i, q, qd, ob);
@@ -284,13 +286,13 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
     static_assert(step_smem_bytes<T, TASK, CTRL>() <= SMEM_LIMIT, "solver slab exceeds the per-block shared memory of sm_100");
     extern __shared__ __align__(16) unsigned char s_raw[];
     float* s_io = reinterpret_cast<float*>(s_raw);
-    __shared__ double s_stats[5];
+    __shared__ double s_stats[6];
     const long long row0 = (long long)blockIdx.x * BS;
     const bool mapped = E.perm != nullptr;               // launch-uniform
     const int t = (int)row0 + threadIdx.x;
     const bool valid = t < (mapped ? E.tcount : E.n);
     const int i = (valid && mapped) ? E.perm[E.t0 + t] : t;
-    if (threadIdx.x < 5) s_stats[threadIdx.x] = 0.0;
+    if (threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
     __syncthreads();                                     // s_stats is zeroed before any warp can atomicAdd into it
     const bool first = io.s0 == 0, last = io.s1 == E.P.nsub;      // launch-uniform
     float act[NA];
@@ -298,10 +300,10 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
     float obs[O], ag[G], dg[G], reward = 0.0f;
     unsigned char term = 0, trunc = 0;
     if (valid) {
-        T q[ND], qd[ND], goal[6], target[ND]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+        T q[ND], qd[ND], target[ND], qc[ND]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         Contacts<T> C;
-        C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BS;
-        load_state<T, NOBJ>(E, i, q, qd, ob, goal);
+        C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BS; C.dropped = 0;
+        load_state<T, NOBJ>(E, i, q, qd, ob);
         if (!first) {
 #pragma unroll
             for (int d = 0; d < ND; d++) target[d] = E.target[d * E.n + i];
@@ -310,9 +312,14 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
         float tquat[4];
         if (first && io.target_quat) row_load<4>(io.target_quat, i, tquat);
         const long long clk0 = E.dbg ? clock64() : 0;
-        env_step<T, TASK, CTRL>(E.M, E.S, E.reward_type, q, qd, ob, goal, act, (first && io.target_quat) ? tquat : nullptr, obs, ag, dg, reward, term, C, sched_key,
-                                target, io.s0, io.s1, E.P.nsub, E.P.thr32);
+        env_step_sim<T, TASK, CTRL>(E.M, E.S, q, qd, ob, act, (first && io.target_quat) ? tquat : nullptr, C, sched_key, target, qc, io.s0, io.s1, E.P.nsub);
         if (E.dbg) { E.dbg[2 * (size_t)(E.t0 + t)] = clock64() - clk0; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); E.dbg[2 * (size_t)(E.t0 + t) + 1] = (long long)sched_key | ((long long)smid << 16); }
+        if (C.dropped > 0) atomicAdd(&s_stats[5], (double)C.dropped);
+        double goal[6];
+        if (last) {     // the goal is only needed now: loaded after the simulation so that it does not occupy registers across the solver
+            load_goal(E, i, goal);
+            env_step_finish<T, TASK>(E.M, E.reward_type, q, qd, qc, ob, goal, E.P.thr64, obs, ag, dg, reward, term);
+        }
         if (last) {
             int steps = E.steps[i] + 1;
             trunc = steps >= task_max_steps(TASK);
@@ -341,7 +348,11 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
         store_state<T, NOBJ>(E, i, q, qd, ob);
         E.ccount[i] = (unsigned short)sched_key;
     }
-    if (!last) return;
+    if (!last) {        // (launch-uniform) only the overflow counter can be non-zero before the step's last segment
+        __syncthreads();
+        if (threadIdx.x == 5 && s_stats[5] != 0.0) atomicAdd(&E.stats[5], s_stats[5]);
+        return;
+    }
     __syncthreads();    // the solver slab is dead for every thread of the block: reuse it as the output tile
     if (mapped) {
         if (valid) { row_store<O>(io.obs, i, obs); row_store<G>(io.ag, i, ag); row_store<G>(io.dg, i, dg); }
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
         if (io.truncated) io.truncated[i] = trunc;
     }
     __syncthreads();
-    if (threadIdx.x < 5 && s_stats[threadIdx.x] != 0.0) atomicAdd(&E.stats[threadIdx.x], s_stats[threadIdx.x]);
+    if (threadIdx.x < 6 && s_stats[threadIdx.x] != 0.0) atomicAdd(&E.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------- raw state exchange / IK
@@ -380,7 +391,7 @@ __global__ void __launch_bounds__(BLOCK) set_state_kernel(const __grid_constant_
     const double* r = in + (size_t)i * SD; const int n = E.n;
     for (int d = 0; d < ND; d++) { E.q[d * n + i] = (T)r[d]; E.qd[d * n + i] = (T)r[9 + d]; }
     for (int k = 0; k < 13 * nobj; k++) E.obj[(size_t)k * n + i] = (T)r[18 + k];
-    for (int k = 0; k < G; k++) E.goal[k * n + i] = (T)r[18 + 13 * nobj + k];
+    for (int k = 0; k < G; k++) E.goal[k * n + i] = r[18 + 13 * nobj + k];
     E.steps[i] = (int)r[SD - 1];
 }
 // calculateInverseKinematics (pybullet.py:479-497) on `link` from the current joint state: target [n,3] + quaternion [n,4] (normalised
@@ -428,10 +439,10 @@ __global__ void __launch_bounds__(BARE_BLOCK) bare_step_kernel(const __grid_cons
     const int i = blockIdx.x * BARE_BLOCK + threadIdx.x;
     if (i >= E.n) return;
     const int n = E.n;
-    T q[ND], qd[ND], goal[6], target[ND], mot[27]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+    T q[ND], qd[ND], target[ND], mot[27]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
     Contacts<T> C;
-    C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BARE_BLOCK;
-    load_state<T, NOBJ>(E, i, q, qd, ob, goal);
+    C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BARE_BLOCK; C.dropped = 0;
+    load_state<T, NOBJ>(E, i, q, qd, ob);
     Model<T> M = E.M;
 #pragma unroll
     for (int d = 0; d < ND; d++) {
@@ -529,23 +540,63 @@ __global__ void __launch_bounds__(256) reward_kernel(const E* __restrict__ ag, c
 // Task.compute_reward, tasks/*.py, on the relabelled batch).  For sampled transition j: the new desired goal is the next achieved
 // goal of transition goal_src[j] (a later step of the same episode under the "future" strategy), or the stored desired goal when
 // goal_src[j] < 0; the reward is recomputed from the transition's own next achieved goal and the new goal, in the reference's
-// float32 arithmetic.  One thread per sampled transition; row gathers (12-24 B rows), 56 / 92 algorithmic bytes per transition.
-template <typename E, int TASK>
+// float32 arithmetic.  56 / 92 algorithmic bytes per transition (3-D / 6-D goals).
+//
+// The kernel is a random row gather: what it moves through DRAM is 32-byte sectors, not rows.  A row of G elements at a pitch of
+// `pitch` elements is fetched with the widest loads its alignment allows (VB bytes each: 16 for 32-byte padded rows, 8 for dense
+// 6-D fp32 rows, 4 otherwise) -- a dense 24-byte row is 3 requests instead of 6 and straddles two sectors half the time, a row
+// padded to 32 bytes (pitch 8) is exactly one sector -- and every thread keeps HT transitions in flight (2 x HT independent row
+// gathers issued before the first use), because a gather is bounded by the number of sectors in flight per SM, not by bandwidth.
+template <typename E, int G, int VB> struct RowLoad {
+    static constexpr int EV = VB / (int)sizeof(E);            // elements per load
+    static constexpr int NV = (G + EV - 1) / EV;               // loads per row (the last one may read padding: only when pitch allows it)
+    __device__ static __forceinline__ void load(const E* __restrict__ p, E* out) {
+        if constexpr (VB == 16) {
+            union { float4 v[NV]; E e[NV * EV]; } u;
+#pragma unroll
+            for (int k = 0; k < NV; k++) u.v[k] = __ldg(reinterpret_cast<const float4*>(p) + k);
+#pragma unroll
+            for (int k = 0; k < G; k++) out[k] = u.e[k];
+        } else if constexpr (VB == 8) {
+            union { float2 v[NV]; E e[NV * EV]; } u;
+#pragma unroll
+            for (int k = 0; k < NV; k++) u.v[k] = __ldg(reinterpret_cast<const float2*>(p) + k);
+#pragma unroll
+            for (int k = 0; k < G; k++) out[k] = u.e[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; k++) out[k] = __ldg(p + k);
+        }
+    }
+};
+constexpr int HER_INFLIGHT = 4;
+template <typename E, int TASK, int VB>
 __global__ void __launch_bounds__(256) her_relabel_kernel(const E* __restrict__ next_ag, const E* __restrict__ dg, const long long* __restrict__ src,
                                                           const long long* __restrict__ goal_src, E* __restrict__ dg_out, E* __restrict__ ag_out,
-                                                          float* __restrict__ reward, long long m, int reward_type, double threshold) {
-    constexpr int G = task_goal_dim(TASK);
+                                                          float* __restrict__ reward, long long m, long long pitch, int reward_type, double threshold) {
+    constexpr int G = task_goal_dim(TASK), HT = HER_INFLIGHT;
+    using RL = RowLoad<E, G, VB>;
     const E thr = (E)threshold;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
-        const long long s = src[j], gs = goal_src[j];
-        const E* pg = gs >= 0 ? next_ag + gs * G : dg + s * G;
-        E a[G], b[G];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; j0 < m; j0 += HT * stride) {
+        long long s[HT], gs[HT];
 #pragma unroll
-        for (int k = 0; k < G; k++) { a[k] = next_ag[s * G + k]; b[k] = pg[k]; }
-        E d = goal_distance(TASK, a, b);
-        reward[j] = reward_from_distance(reward_type, d, thr);
+        for (int h = 0; h < HT; h++) { const long long j = j0 + h * stride; const bool ok = j < m; s[h] = ok ? __ldcs(src + j) : 0; gs[h] = ok ? __ldcs(goal_src + j) : 0; }
+        E a[HT][G], b[HT][G];
 #pragma unroll
-        for (int k = 0; k < G; k++) { dg_out[j * G + k] = b[k]; if (ag_out) ag_out[j * G + k] = a[k]; }
+        for (int h = 0; h < HT; h++) {
+            RL::load(next_ag + s[h] * pitch, a[h]);
+            RL::load(gs[h] >= 0 ? next_ag + gs[h] * pitch : dg + s[h] * pitch, b[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < HT; h++) {
+            const long long j = j0 + h * stride;
+            if (j >= m) break;
+            E d = goal_distance(TASK, a[h], b[h]);
+            __stcs(reward + j, reward_from_distance(reward_type, d, thr));
+#pragma unroll
+            for (int k = 0; k < G; k++) { __stcs(dg_out + j * G + k, b[h][k]); if (ag_out) __stcs(ag_out + j * G + k, a[h][k]); }
+        }
     }
 }
 

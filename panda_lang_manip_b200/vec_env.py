@@ -272,6 +272,14 @@ class PandaVecEnv:
         _lib.check(self.lib.pg_diverged(self._h, ctypes.byref(c)))
         return int(c.value)
 
+    def contact_overflows(self) -> int:
+        """Contact candidates dropped at the per-sub-step cap of the on-chip contact store since creation (10 / 22 for Stack)."""
+        import ctypes
+        torch.cuda.current_stream(self.device).synchronize()
+        c = ctypes.c_longlong()
+        _lib.check(self.lib.pg_contact_overflows(self._h, ctypes.byref(c)))
+        return int(c.value)
+
     def stats(self) -> np.ndarray:
         """{episodes, successes, return_sum, length_sum} accumulated by auto-reset on this device."""
         import ctypes
@@ -319,13 +327,26 @@ def her_relabel(task: str, reward_type: str, next_achieved_goal: torch.Tensor, d
     examples/train_push.py:1-12 sets up stable-baselines3's HerReplayBuffer, which does this with a numpy gather and
     ``env.compute_reward``).  ``next_achieved_goal`` / ``desired_goal`` are the replay buffer's goal arrays flattened to [R, G];
     ``src`` [M] indexes the sampled transitions and ``goal_src`` [M] the transitions whose next achieved goal becomes the new goal
-    (negative: keep the stored goal).  Returns (new_desired_goal [M, G], reward [M] float32[, next_achieved_goal[src] [M, G]])."""
+    (negative: keep the stored goal).  Returns (new_desired_goal [M, G], reward [M] float32[, next_achieved_goal[src] [M, G]]).
+    Goal arrays passed as ``padded[:, :G]`` views of a buffer with 32-byte rows (``torch.zeros(R, 8)`` for fp32) are gathered in place,
+    one DRAM sector per row."""
     if not (torch.is_tensor(next_achieved_goal) and next_achieved_goal.is_cuda):
         raise _lib.PandaB200Error("her_relabel takes CUDA tensors: the replay buffer lives in HBM")
     g = {"stack": 6, "flip": 4}.get(task, 3)
     dt = torch.float64 if next_achieved_goal.dtype == torch.float64 else torch.float32
-    a = next_achieved_goal.to(dt).reshape(-1, g).contiguous()
-    d = desired_goal.to(device=a.device, dtype=dt).reshape(-1, g).contiguous()
+
+    def rows(t):
+        """[R, G] view and its row pitch in elements: a 2-D tensor whose rows are unit-stride slices of a wider (padded) buffer is used
+        in place (pg_her_relabel_pitched); anything else is flattened to dense rows."""
+        t = t.to(device=next_achieved_goal.device, dtype=dt)
+        if t.dim() == 2 and t.shape[1] == g and t.stride(1) == 1 and t.stride(0) >= g:
+            return t, t.stride(0)
+        t = t.reshape(-1, g).contiguous()
+        return t, g
+    a, pa = rows(next_achieved_goal)
+    d, pd = rows(desired_goal)
+    if pa != pd:                                        # one pitch for both arrays
+        a, d, pa = a.contiguous(), d.contiguous(), g
     if a.shape != d.shape:
         raise ValueError("next_achieved_goal and desired_goal must have the same [R, G] shape")
     s_ = src.to(device=a.device, dtype=torch.long).contiguous()
@@ -337,9 +358,9 @@ def her_relabel(task: str, reward_type: str, next_achieved_goal: torch.Tensor, d
     ag_out = torch.empty((m, g), dtype=dt, device=a.device) if return_achieved else None
     rew = torch.empty((m,), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        _lib.check(_lib.load().pg_her_relabel_t(_lib.TASKS[task], _lib.REWARD[reward_type], DEFAULT_THRESHOLD[task] if threshold is None else float(threshold),
-                                                _ptr(a), _ptr(d), _ptr(s_), _ptr(gs), _ptr(new_dg), _ptr(ag_out), _ptr(rew),
-                                              m, 1 if dt == torch.float64 else 0, torch.cuda.current_stream(a.device).cuda_stream))
+        _lib.check(_lib.load().pg_her_relabel_pitched(_lib.TASKS[task], _lib.REWARD[reward_type], DEFAULT_THRESHOLD[task] if threshold is None else float(threshold),
+                                                      _ptr(a), _ptr(d), pa, _ptr(s_), _ptr(gs), _ptr(new_dg), _ptr(ag_out), _ptr(rew),
+                                                      m, 1 if dt == torch.float64 else 0, torch.cuda.current_stream(a.device).cuda_stream))
     return (new_dg, rew, ag_out) if return_achieved else (new_dg, rew)
 
 

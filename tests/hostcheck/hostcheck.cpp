@@ -40,10 +40,10 @@ template <typename T> static void ik(const double* base, const double* q, const 
 template <typename T, int TASK, int CTRL> static void env_step_t(int reward, const double* base, double* st, const float* action, float* obs, float* ag, float* dg, float* rew, unsigned char* succ) {
     Model<T> M = make_model<T>(base); Scene<T> S = make_scene<T>(TASK);
     constexpr int NOBJ = task_nobj(TASK);
-    T q[ND], qd[ND], goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+    T q[ND], qd[ND]; double goal[6]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
     for (int i = 0; i < ND; i++) { q[i] = (T)st[i]; qd[i] = (T)st[9 + i]; }
     for (int o = 0; o < NOBJ; o++) { const double* p = st + 18 + 13 * o; ob[o].pos = mk<T>((T)p[0], (T)p[1], (T)p[2]); ob[o].qx = (T)p[3]; ob[o].qy = (T)p[4]; ob[o].qz = (T)p[5]; ob[o].qw = (T)p[6]; ob[o].lin = mk<T>((T)p[7], (T)p[8], (T)p[9]); ob[o].ang = mk<T>((T)p[10], (T)p[11], (T)p[12]); }
-    for (int k = 0; k < 6; k++) goal[k] = (T)st[44 + k];
+    for (int k = 0; k < 6; k++) goal[k] = st[44 + k];
     static Contacts<T> C; static T slab[solver_slots(2)]; C.st.base = slab; C.st.stride = 1;
     int mc = 0; T target[ND]; env_step<T, TASK, CTRL>(M, S, reward, q, qd, ob, goal, action, nullptr, obs, ag, dg, *rew, *succ, C, mc, target);
     for (int i = 0; i < ND; i++) { st[i] = q[i]; st[9 + i] = qd[i]; }

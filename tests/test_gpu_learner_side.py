@@ -35,6 +35,16 @@ def test_her_relabel_matches_reference_arithmetic(task, g, reward_type, dtype):
         assert np.allclose(got, want_r, rtol=0, atol=2e-7 if dtype == np.float32 else 1e-7)
     else:
         assert got.tobytes() == want_r.tobytes()
+    # the same gather from goal arrays stored with padded (32-byte for fp32) rows, and from a misaligned dense view (scalar-load path)
+    pad = 8 if dtype == np.float32 else 6 + (g % 2)
+    nag_p = torch.zeros((R, pad), dtype=torch.from_numpy(nag).dtype, device="cuda"); dg_p = torch.zeros_like(nag_p)
+    nag_p[:, :g] = torch.from_numpy(nag).cuda(); dg_p[:, :g] = torch.from_numpy(dg).cuda()
+    p_dg, p_rew, p_ag = p.her_relabel(task, reward_type, nag_p[:, :g], dg_p[:, :g], torch.from_numpy(src).cuda(), torch.from_numpy(gsrc).cuda(), return_achieved=True)
+    assert torch.equal(p_dg, new_dg) and torch.equal(p_ag, ag) and p_rew.cpu().numpy().tobytes() == got.tobytes()
+    flat = torch.zeros(R * g + 1, dtype=nag_p.dtype, device="cuda"); flat2 = torch.zeros_like(flat)
+    flat[1:] = torch.from_numpy(nag).cuda().reshape(-1); flat2[1:] = torch.from_numpy(dg).cuda().reshape(-1)
+    u_dg, u_rew = p.her_relabel(task, reward_type, flat[1:].view(R, g), flat2[1:].view(R, g), torch.from_numpy(src).cuda(), torch.from_numpy(gsrc).cuda())
+    assert torch.equal(u_dg, new_dg) and u_rew.cpu().numpy().tobytes() == got.tobytes()
     # empty batch
     e_dg, e_r = p.her_relabel(task, reward_type, torch.from_numpy(nag).cuda(), torch.from_numpy(dg).cuda(), torch.zeros(0, dtype=torch.long, device="cuda"),
                               torch.zeros(0, dtype=torch.long, device="cuda"))

@@ -58,8 +58,10 @@ def _rollout(task, control, n_envs, steps, precision="f32", seed=0, action_scale
                 eo = np.abs(st[i, 18 + 13 * o:18 + 13 * o + 7] - oe.object_state(o)[:7]).max()
                 errs["obj"] = max(errs["obj"], eo); errs["obj_env"][i] = max(errs["obj_env"][i], eo)
             # reward / success of EVERY env at EVERY step, teacher-forced or free-running: bit-exact against the reference's arithmetic
-            # (numpy) on the float32 goals the kernel itself emitted ...
-            r_np, s_np = reward_np(task, "sparse", ag_g[i], dg_g[i])
+            # (numpy) on the inputs RobotTaskEnv.step passes (core.py:285-288): the float32 achieved goal the kernel itself emitted and
+            # the task's FLOAT64 goal (numpy promotes the distance to float64) ...
+            g0 = 18 + 13 * nobj
+            r_np, s_np = reward_np(task, "sparse", ag_g[i], st[i, g0:g0 + GOAL_DIM[task]])
             errs["rew"] += int(np.float32(rew_g[i]).tobytes() != np.float32(r_np).tobytes()); errs["succ"] += int(bool(term_g[i]) != bool(s_np))
             errs["compared"] += 1
             # ... and against the oracle's own decision, unless the oracle's distance sits within 1 mm of the threshold (an fp32 state
