@@ -462,22 +462,18 @@ PG_HD void contact_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpa
 // One 2 ms stepSimulation: unconstrained velocities, contact generation at the current poses, <= 50 sequential-impulse sweeps
 // over [joint limits, motors] (direction alternating), contact normals, friction cones; exit when the largest squared
 // velocity change of a sweep is <= 1e-7; semi-implicit Euler.
-// The sequential-impulse loop.  WATCH (the env path): while `fast`, the 14 arm limit rows are only watched; returns true if one of them
-// would have engaged (the caller then restarts with fast = false, which sweeps every row with the rolled full sweep over the scratch
-// record L).  One instantiation per kernel: the contact code below exists once, only the joint-row part differs between the modes.
-// !WATCH (bare worlds): the unrolled full sweep.
-template <typename T, int NOBJ, bool WATCH>
+// The sequential-impulse loop.  FAST: the 14 arm limit rows are only watched; returns true if one of them would have engaged
+// (the caller then restarts with FAST = false).  Two instantiations, so the hot loop carries only the rows it executes.
+template <typename T, int NOBJ, bool FAST>
 PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const T (*Minv)[ND], JointRows<T>& R,
-                     Contacts<T>& C, const Obj<T>* ob, const bool robot_contacts, T* dvq, V3<T>* dvl, V3<T>* dva, const bool fast, RolledRows<T>* L) {
+                     Contacts<T>& C, const Obj<T>* ob, const bool robot_contacts, T* dvq, V3<T>* dvl, V3<T>* dva) {
     const int nc = C.n;
     bool live = false;
     int it = 0;
     for (; it < 50; it++) {
         T res = T(0), watch = T(0);
-        if (!WATCH) joint_rows_sweep<false>(M, Minv, R, dvq, it, res, watch);
-        else if (fast) joint_rows_sweep<true>(M, Minv, R, dvq, it, res, watch);
-        else joint_rows_sweep_rolled(*L, dvq, it, res);
-        if (WATCH && fast && watch > T(0)) { live = true; break; }
+        joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, watch);
+        if (FAST && watch > T(0)) { live = true; break; }
         if (nc > 0) {
             T d8[8], F8[8];
 #pragma unroll
@@ -663,39 +659,33 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
     // Arm limit rows are exact no-ops while they rest at zero impulse: the fast solve only watches them and, if one would engage,
-    // the solve restarts from zero impulses with every row real (the rolled full sweep).  Which of the two ran is a function of the
-    // env's own state, never of the batch or the schedule.
+    // the solve restarts from zero impulses with every row real (a watched row is an exact no-op: the result is the full sweep's, up to
+    // FMA-contraction differences between the two loop instantiations).  Which of the two ran is a function of the env's own state,
+    // never of the batch or the schedule.
     const int nc = C.n;
     bool fast = WATCH_LIMITS && !full_sweep && !arm_limit_violated(M, q);
 #ifdef PG_HOST_DEBUG
     if (!fast) g_dbg_full_starts++;
 #endif
-    if (!WATCH_LIMITS) pgs_solve<T, NOBJ, false>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva, false, nullptr);
-    else {
-        RolledRows<T> L;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; attempt++) {
-            if (!fast) rolled_fill(M, Minv, R, L);
-            const bool live = pgs_solve<T, NOBJ, true>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva, fast, &L);
-            if (!live) break;
-            // a watched row would have engaged: start over with every row real
+    bool live = false;
+    if (fast) live = pgs_solve<T, NOBJ, true>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+    if (!fast || live) {
+        full_sweep = true;
+        if (live) {
 #ifdef PG_HOST_DEBUG
             g_dbg_fallbacks++;
 #endif
-            fast = false; limits_active = true;
 #pragma unroll
             for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
 #pragma unroll
             for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
             for (int c = 0; c < nc; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
         }
-        if (!fast) {
-            full_sweep = true;
-            bool any = false;       // did an arm limit row actually carry impulse?  (decides whether the next step starts with the full sweep)
-#pragma unroll 1
-            for (int r = 0; r < 14; r++) any = any || L.lim_app[r] > T(0);
-            limits_active = limits_active || any;
-        }
+        pgs_solve<T, NOBJ, false>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+        bool any = false;       // did an arm limit row actually carry impulse?  (decides whether the next step starts with the full sweep)
+#pragma unroll
+        for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
+        limits_active = limits_active || any || live;
     }
 #pragma unroll
     for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }

@@ -682,66 +682,6 @@ template <bool FAST, typename T> PG_HD void joint_rows_sweep(const Model<T>& M, 
     if (it & 1) { RowsFwd<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); RowsFwd<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); }
     else { RowsRev<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); RowsRev<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); }
 }
-// The full sweep (every limit row real) as a ROLLED loop over joints: the fallback of the watched sweep.  It runs only for envs
-// whose arm joint limits engage (never in random-action rollouts, sometimes under scripted policies), so it is written for code
-// size, not speed: ~150 instructions instead of a second fully unrolled solver loop, which is what made the watched sweep a net
-// loss for ee control in round 1 (two instantiations of the contact code in one kernel).  The rows live in a per-thread scratch
-// record (local memory: runtime-indexed), filled from the register-resident rows when an env enters the fallback; the arithmetic per
-// row is limit_pair / motor_row's.
-template <typename T> struct RolledRows { T Minv[ND * ND], lim_rhs[2 * ND], lim_app[2 * ND], mot_rhs[ND], mot_app[ND], invD[ND], max_imp[ND], dv[ND]; };
-template <typename T> PG_HD void rolled_fill(const Model<T>& M, const T (*Minv)[ND], const JointRows<T>& R, RolledRows<T>& L) {
-#pragma unroll
-    for (int d = 0; d < ND; d++) {
-#pragma unroll
-        for (int k = 0; k < ND; k++) L.Minv[ND * k + d] = Minv[k][d];
-        L.lim_rhs[2 * d] = R.lim_rhs[2 * d]; L.lim_rhs[2 * d + 1] = R.lim_rhs[2 * d + 1]; L.lim_app[2 * d] = T(0); L.lim_app[2 * d + 1] = T(0);
-        L.mot_rhs[d] = R.mot_rhs[d]; L.mot_app[d] = T(0); L.invD[d] = R.invD[d]; L.max_imp[d] = M.max_imp[d];
-    }
-}
-template <typename T> PG_HD void rolled_limit_pair(RolledRows<T>& L, int D, int first, T& res) {
-    T w = T(0);
-    const T mdd = L.Minv[ND * D + D];
-#pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-        const int side = h == 0 ? first : 1 - first;
-        const T sg = side == 0 ? T(1) : T(-1);
-        const T app = L.lim_app[2 * D + side];
-        const T di = fmin(fmax(L.lim_rhs[2 * D + side] - sg * L.dv[D] * L.invD[D], -app), T(100) - app);
-        L.lim_app[2 * D + side] = app + di;
-        const T wi = sg * di;
-        L.dv[D] += mdd * wi;
-        w += wi;
-        res = fmax(res, fabs(di * mdd));
-    }
-#pragma unroll 1
-    for (int k = 0; k < ND; k++) if (k != D) L.dv[k] += L.Minv[ND * k + D] * w;
-}
-template <typename T> PG_HD void rolled_motor_row(RolledRows<T>& L, int D, T& res) {
-    const T app = L.mot_app[D], mx = L.max_imp[D];
-    const T di = fmin(fmax(L.mot_rhs[D] - L.dv[D] * L.invD[D], -mx - app), mx - app);
-    L.mot_app[D] = app + di;
-#pragma unroll 1
-    for (int k = 0; k < ND; k++) L.dv[k] += L.Minv[ND * k + D] * di;
-    res = fmax(res, fabs(di * L.Minv[ND * D + D]));
-}
-// one full sweep over the non-contact rows in Bullet's order (see joint_rows_sweep); dv travels through the scratch record
-template <typename T> PG_HD void joint_rows_sweep_rolled(RolledRows<T>& L, T* dv, int it, T& res) {
-#pragma unroll
-    for (int d = 0; d < ND; d++) L.dv[d] = dv[d];
-    if (it & 1) {
-#pragma unroll 1
-        for (int D = 0; D < ND; D++) rolled_limit_pair(L, D, 0, res);
-#pragma unroll 1
-        for (int D = 0; D < ND; D++) rolled_motor_row(L, D, res);
-    } else {
-#pragma unroll 1
-        for (int D = ND - 1; D >= 0; D--) rolled_motor_row(L, D, res);
-#pragma unroll 1
-        for (int D = ND - 1; D >= 0; D--) rolled_limit_pair(L, D, 1, res);
-    }
-#pragma unroll
-    for (int d = 0; d < ND; d++) dv[d] = L.dv[d];
-}
 // true when an arm joint sits on or beyond a limit at set-up: its row is live from the start, use the full sweep
 template <typename T> PG_HD bool arm_limit_violated(const Model<T>& M, const T* q) {
     bool v = false;

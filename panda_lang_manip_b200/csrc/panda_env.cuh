@@ -209,9 +209,10 @@ PG_HD void env_step_sim(const Model<T>& M, const Scene<T>& S, T* q, T* qd, Obj<T
 #pragma unroll
             for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
         }
-        // watched arm-limit rows for both control types: the fallback is the rolled full sweep (joint_rows_sweep_rolled), so the kernel holds
-        // one solver loop and one copy of the contact code (round 1 carried a second unrolled instantiation, which cost ee control 13 %)
-        env_substep<T, NOBJ, true>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
+        // watched arm-limit rows: a measured policy -- +25 % with joint control, -13 % with ee control (contact rows dominate there and the
+        // second solver instantiation schedules worse), so it is enabled for joint control only.  A rolled (local-memory) full-sweep
+        // fallback inside one solver loop was tried in round 2: 3-10x slower (local loads / stores inside the sweep loop), removed.
+        env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
         if (C.n > 0) nsub_contact++;
         near = near || C.near;
     }

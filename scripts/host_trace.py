@@ -41,3 +41,5 @@ print(f"{task}/{ctrl}: {len(tr)} sub-steps; robot-contact share {np.mean(nr > 0)
 for name, m in (("nr>0", nr > 0), ("nr==0,nc>0", (nr == 0) & (nc > 0)), ("nc==0", nc == 0)):
     if m.any(): print(f"  {name}: share {m.mean():.3f} mean contacts {nc[m].mean():.1f} (robot {nr[m].mean():.1f}) mean sweeps {it[m].mean() + 1:.1f} capped {np.mean(it[m] >= 49):.2f}")
 print("  nc histogram:", np.bincount(nc, minlength=11)[:24])
+hc.hc_dbg_fallbacks.restype = ctypes.c_long; hc.hc_dbg_full_starts.restype = ctypes.c_long
+print("  watched-sweep fallbacks", hc.hc_dbg_fallbacks(), "solves started with the full sweep", hc.hc_dbg_full_starts())
