@@ -382,7 +382,7 @@ template <typename T> PG_HD T dot8(const T* a, const T* b) {
 }
 
 // 1/D and rhs of the three rows of every contact (setupMultiBodyContactConstraint: speculative when separated, ERP when penetrating)
-template <typename T, int NOBJ>
+template <typename T, int NOBJ, bool ROBOT = true>
 PG_HD void rows_setup(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const Obj<T>* ob, Contacts<T>& C) {
     for (int c = 0; c < C.n; c++) {
         ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
@@ -393,11 +393,13 @@ PG_HD void rows_setup(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<
         for (int k = 0; k < 3; k++) {
             V3<T> d = k == 0 ? X.n : (k == 1 ? t1 : t2);
             T den = T(0), rel = T(0);
-            if (NOBJ == 0 || (X.table && X.rb >= 0)) {
-                if (k == 0) { AxisRow<2, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
-                else if (k == 1) { AxisRow<1, -1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
-                else { AxisRow<0, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
-            } else if (X.rb >= 0) { T w[8], y[8]; robot_wrench<T, NOBJ>(Op, X, d, w); lambda_mul(Op, w, y); den += dot8(w, y); rel += dot8(w, Op.v); }
+            if (ROBOT) {
+                if (NOBJ == 0 || (X.table && X.rb >= 0)) {
+                    if (k == 0) { AxisRow<2, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+                    else if (k == 1) { AxisRow<1, -1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+                    else { AxisRow<0, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+                } else if (X.rb >= 0) { T w[8], y[8]; robot_wrench<T, NOBJ>(Op, X, d, w); lambda_mul(Op, w, y); den += dot8(w, y); rel += dot8(w, Op.v); }
+            }
 #pragma unroll
             for (int o = 0; o < NOBJ; o++) {
                 if (X.sgo[o] != T(0)) {
@@ -464,7 +466,9 @@ PG_HD void contact_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpa
 // velocity change of a sweep is <= 1e-7; semi-implicit Euler.
 // The sequential-impulse loop.  FAST: the 14 arm limit rows are only watched; returns true if one of them would have engaged
 // (the caller then restarts with FAST = false).  Two instantiations, so the hot loop carries only the rows it executes.
-template <typename T, int NOBJ, bool FAST>
+// ROBOT = false (the light path of the split scheme below): no robot box is in contact, so the operational-space code, the robot-on-table
+// rows and (with one object) the generic rows do not exist in the instantiation -- the contacts are object vertices on a plane only.
+template <typename T, int NOBJ, bool FAST, bool ROBOT = true>
 PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const T (*Minv)[ND], JointRows<T>& R,
                      Contacts<T>& C, const Obj<T>* ob, const bool robot_contacts, T* dvq, V3<T>* dvl, V3<T>* dva) {
     const int nc = C.n;
@@ -474,11 +478,11 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
         T res = T(0), watch = T(0);
         joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, watch);
         if (FAST && watch > T(0)) { live = true; break; }
-        if (nc > 0) {
+        if ((ROBOT || NOBJ > 0) && nc > 0) {
             T d8[8], F8[8];
 #pragma unroll
             for (int a = 0; a < 8; a++) { d8[a] = T(0); F8[a] = T(0); }
-            if (robot_contacts) {       // operational-space velocity change so far: Jx dvq
+            if (ROBOT && robot_contacts) {       // operational-space velocity change so far: Jx dvq
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
 #pragma unroll
@@ -489,12 +493,12 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
             // Typed passes: the three kinds of contact run different row code, and a warp pays for every kind present in any of its
             // lanes at a given contact index; looping kind by kind (collection order = kind order, so the row order is unchanged)
             // makes lanes meet in the same code even when their counts differ.
-            const int eB = NOBJ > 0 ? C.nB : 0, eA = NOBJ > 0 ? C.nB + C.nA : nc;
+            const int eB = !ROBOT ? nc : (NOBJ > 0 ? C.nB : 0), eA = !ROBOT ? nc : (NOBJ > 0 ? C.nB + C.nA : nc);
             auto normal_row = [&](int c, auto kind) {
                 constexpr int K = decltype(kind)::value;
                 ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
-                T app = C.f(c, C_APP), inv = C.f(c, C_INVD), di;
-                if constexpr (K == KIND_ROBOT_TABLE) {
+                T app = C.f(c, C_APP), inv = C.f(c, C_INVD), di = T(0);
+                if constexpr (K == KIND_ROBOT_TABLE && ROBOT) {
                     AxisRow<2, 1, T, NOBJ> row(Op, X);
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - row.jdv(d8) * inv;
                     di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
@@ -507,7 +511,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
                     C.f(c, C_APP) = app + di;
                     row.apply(W.Iinv[o], T(1) / S.mass[o], di, dvl[o], dva[o]);
-                } else {
+                } else if constexpr (ROBOT) {
                     T jd = dot(X.n, contact_dv<T, NOBJ>(Op, X, d8, dvl, dva, ob));
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - jd * inv;
                     di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
@@ -522,7 +526,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                 if (napp <= T(0)) return;
                 ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
                 T a1 = C.f(c, C_APP + 1), a2 = C.f(c, C_APP + 2), i1 = C.f(c, C_INVD + 1), i2 = C.f(c, C_INVD + 2);
-                T lim = C.f(c, C_MU) * napp, d1, d2;
+                T lim = C.f(c, C_MU) * napp, d1 = T(0), d2 = T(0);
                 if constexpr (K == KIND_OBJ_PLANE) {
                     const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
                     V3<T> r = X.P - ob[o].pos;
@@ -534,7 +538,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                     C.f(c, C_APP + 1) = s1; C.f(c, C_APP + 2) = s2;
                     const T im = T(1) / S.mass[o];
                     r1.apply(W.Iinv[o], im, d1, dvl[o], dva[o]); r2.apply(W.Iinv[o], im, d2, dvl[o], dva[o]);
-                } else if constexpr (K == KIND_ROBOT_TABLE) {
+                } else if constexpr (K == KIND_ROBOT_TABLE && ROBOT) {
                     AxisRow<1, -1, T, NOBJ> r1(Op, X); AxisRow<0, 1, T, NOBJ> r2(Op, X);
                     T s1 = a1 + C.f(c, C_RHS + 1) - r1.jdv(d8) * i1, s2 = a2 + C.f(c, C_RHS + 2) - r2.jdv(d8) * i2;
                     T len = sqrt(s1 * s1 + s2 * s2);
@@ -555,7 +559,7 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
                             F8[k] += w[k];
                         }
                     }
-                } else {
+                } else if constexpr (ROBOT) {
                     V3<T> t1, t2; plane_space(X.n, t1, t2);
                     const V3<T> u = contact_dv<T, NOBJ>(Op, X, d8, dvl, dva, ob);
                     T j1 = dot(t1, u), j2 = dot(t2, u);
@@ -571,14 +575,14 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
             {
                 int c = 0;
                 if (NOBJ > 0) for (; c < eB; c++) normal_row(c, KindTag<KIND_OBJ_PLANE>{});
-                for (; c < eA; c++) normal_row(c, KindTag<KIND_ROBOT_TABLE>{});
-                if (NOBJ > 0) for (; c < nc; c++) normal_row(c, KindTag<KIND_GENERIC>{});
+                if (ROBOT) for (; c < eA; c++) normal_row(c, KindTag<KIND_ROBOT_TABLE>{});
+                if (ROBOT && NOBJ > 0) for (; c < nc; c++) normal_row(c, KindTag<KIND_GENERIC>{});
                 c = 0;
                 if (NOBJ > 0) for (; c < eB; c++) friction_rows(c, KindTag<KIND_OBJ_PLANE>{});
-                for (; c < eA; c++) friction_rows(c, KindTag<KIND_ROBOT_TABLE>{});
-                if (NOBJ > 0) for (; c < nc; c++) friction_rows(c, KindTag<KIND_GENERIC>{});
+                if (ROBOT) for (; c < eA; c++) friction_rows(c, KindTag<KIND_ROBOT_TABLE>{});
+                if (ROBOT && NOBJ > 0) for (; c < nc; c++) friction_rows(c, KindTag<KIND_GENERIC>{});
             }
-            if (robot_contacts) {       // fold this sweep's contact wrench back into the joint velocities: dvq += M^-1 Jx^T F8
+            if (ROBOT && robot_contacts) {       // fold this sweep's contact wrench back into the joint velocities: dvq += M^-1 Jx^T F8
                 T tau[ND];
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
@@ -610,6 +614,34 @@ PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>&
     return live;
 }
 
+// world frames of the arm links and of the robot's collision boxes from the joints' sines / cosines
+template <typename T, int NOBJ>
+PG_HD void world_robot(const Model<T>& M, const Scene<T>& S, const T* q, const T* sn, const T* cs, World<T, NOBJ>& W) {
+    Frame<T> B; B.X = mk<T>(1, 0, 0); B.Y = mk<T>(0, 1, 0); B.Z = mk<T>(0, 0, 1); B.p = ld3(M.base);
+    W.F[0] = fk_next<0>(M, B, sn[0], cs[0]); W.F[1] = fk_next<1>(M, W.F[0], sn[1], cs[1]); W.F[2] = fk_next<2>(M, W.F[1], sn[2], cs[2]);
+    W.F[3] = fk_next<3>(M, W.F[2], sn[3], cs[3]); W.F[4] = fk_next<4>(M, W.F[3], sn[4], cs[4]); W.F[5] = fk_next<5>(M, W.F[4], sn[5], cs[5]);
+    W.F[6] = fk_next<6>(M, W.F[5], sn[6], cs[6]);
+    const T k = Consts<T>::k45;
+    W.Rb.X = (W.F[6].X - W.F[6].Y) * k; W.Rb.Y = (W.F[6].X + W.F[6].Y) * k; W.Rb.Z = W.F[6].Z;
+    V3<T> ph = W.F[6].p + W.F[6].Z * (M.hz - T(0.0584));   // hand frame origin
+    V3<T> pf = W.F[6].p + W.F[6].Z * M.hz;
+    W.cb[0] = ph + rot_mul(W.Rb, ld3(S.rb_c[0]));
+    W.cb[1] = pf + W.Rb.Y * q[7] + rot_mul(W.Rb, ld3(S.rb_c[1]));
+    W.cb[2] = pf - W.Rb.Y * q[8] + rot_mul(W.Rb, ld3(S.rb_c[2]));
+}
+// world inverse inertia of object o from its rotation W.Ro[o]
+template <typename T, int NOBJ>
+PG_HD void world_inertia(const Scene<T>& S, int o, World<T, NOBJ>& W) {
+    const Rot<T>& R = W.Ro[o];
+    T ix = T(1) / S.Ic[o][0], iy = T(1) / S.Ic[o][1], iz = T(1) / S.Ic[o][2];
+    W.Iinv[o][0] = ix * R.X.x * R.X.x + iy * R.Y.x * R.Y.x + iz * R.Z.x * R.Z.x;
+    W.Iinv[o][1] = ix * R.X.x * R.X.y + iy * R.Y.x * R.Y.y + iz * R.Z.x * R.Z.y;
+    W.Iinv[o][2] = ix * R.X.x * R.X.z + iy * R.Y.x * R.Y.z + iz * R.Z.x * R.Z.z;
+    W.Iinv[o][3] = ix * R.X.y * R.X.y + iy * R.Y.y * R.Y.y + iz * R.Z.y * R.Z.y;
+    W.Iinv[o][4] = ix * R.X.y * R.X.z + iy * R.Y.y * R.Y.z + iz * R.Z.y * R.Z.z;
+    W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
+}
+
 template <typename T, int NOBJ, bool WATCH_LIMITS, bool GENERIC_MOTORS = false>
 PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep, bool& limits_active,
                        const T* mot = nullptr) {
@@ -618,31 +650,12 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
 #pragma unroll
     for (int d = 0; d < ND; d++) qd[d] += qdd[d] * Consts<T>::dt;
     World<T, NOBJ> W;
-    {   // world frames from the sines / cosines already computed
-        Frame<T> B; B.X = mk<T>(1, 0, 0); B.Y = mk<T>(0, 1, 0); B.Z = mk<T>(0, 0, 1); B.p = ld3(M.base);
-        W.F[0] = fk_next<0>(M, B, sn[0], cs[0]); W.F[1] = fk_next<1>(M, W.F[0], sn[1], cs[1]); W.F[2] = fk_next<2>(M, W.F[1], sn[2], cs[2]);
-        W.F[3] = fk_next<3>(M, W.F[2], sn[3], cs[3]); W.F[4] = fk_next<4>(M, W.F[3], sn[4], cs[4]); W.F[5] = fk_next<5>(M, W.F[4], sn[5], cs[5]);
-        W.F[6] = fk_next<6>(M, W.F[5], sn[6], cs[6]);
-        const T k = Consts<T>::k45;
-        W.Rb.X = (W.F[6].X - W.F[6].Y) * k; W.Rb.Y = (W.F[6].X + W.F[6].Y) * k; W.Rb.Z = W.F[6].Z;
-        V3<T> ph = W.F[6].p + W.F[6].Z * (M.hz - T(0.0584));   // hand frame origin
-        V3<T> pf = W.F[6].p + W.F[6].Z * M.hz;
-        W.cb[0] = ph + rot_mul(W.Rb, ld3(S.rb_c[0]));
-        W.cb[1] = pf + W.Rb.Y * q[7] + rot_mul(W.Rb, ld3(S.rb_c[1]));
-        W.cb[2] = pf - W.Rb.Y * q[8] + rot_mul(W.Rb, ld3(S.rb_c[2]));
-    }
+    world_robot(M, S, q, sn, cs, W);
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) {
         W.Ro[o] = quat_rot(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw);
         obj_unconstrained(S, o, ob[o], W.Ro[o]);
-        const Rot<T>& R = W.Ro[o];
-        T ix = T(1) / S.Ic[o][0], iy = T(1) / S.Ic[o][1], iz = T(1) / S.Ic[o][2];
-        W.Iinv[o][0] = ix * R.X.x * R.X.x + iy * R.Y.x * R.Y.x + iz * R.Z.x * R.Z.x;
-        W.Iinv[o][1] = ix * R.X.x * R.X.y + iy * R.Y.x * R.Y.y + iz * R.Z.x * R.Z.y;
-        W.Iinv[o][2] = ix * R.X.x * R.X.z + iy * R.Y.x * R.Y.z + iz * R.Z.x * R.Z.z;
-        W.Iinv[o][3] = ix * R.X.y * R.X.y + iy * R.Y.y * R.Y.y + iz * R.Z.y * R.Z.y;
-        W.Iinv[o][4] = ix * R.X.y * R.X.z + iy * R.Y.y * R.Y.z + iz * R.Z.y * R.Z.z;
-        W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
+        world_inertia(S, o, W);
     }
     JointRows<T> R;
     joint_rows_setup<WATCH_LIMITS, GENERIC_MOTORS>(M, q, qd, target, Minv, R, mot);
@@ -691,6 +704,294 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
     for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { ob[o].lin = ob[o].lin + dvl[o]; ob[o].ang = ob[o].ang + dva[o]; obj_integrate(ob[o]); }
+}
+
+
+// ---------------------------------------------------------------------------------------------- split sub-step: light path / heavy path
+// Scenes with at most one object run every sub-step through one of two paths, chosen by the env's own state (never by the batch or the
+// schedule, so results do not depend on how a batch is launched):
+//
+//   light  no robot collision box is in contact and the arm joint limits are slack: the watched-limit sweep plus object-on-plane rows in
+//          the compact operational-space records (pgs_solve<FAST, ROBOT = false>), 17 words of shared memory per contact;
+//   heavy  a robot box touches the table or the object, or an arm limit is engaged: every contact row is set up once per sub-step as a
+//          DENSE row of the constraint Jacobian in the coordinates z = [joint velocities (9), object twist (6)] together with its
+//          impulse response W J^T (heavy_solve).  A row's sweep is then two dot-product-sized loops over shared memory (J z, z += R di)
+//          -- the same code for every contact kind, no operational-space products, no fold-back, no kind divergence inside a warp.
+//          101 words per contact with one object: a launch that may run it gives a 32-env block 151 kB of shared memory.
+//
+// A launch that does not own that much shared memory (the "light" launches of a sorted batch) REFUSES a heavy sub-step before it touches
+// the state; the host side then runs the env in a heavy launch.  The heavy path is a separate, non-inlined function: the light path's
+// register allocation and instruction footprint do not see it.
+#ifdef __CUDACC__
+#define PG_NOINLINE __noinline__
+#else
+#define PG_NOINLINE __attribute__((noinline))
+#endif
+PG_HD constexpr bool dense_supported(int nobj) { return nobj <= 1; }
+PG_HD constexpr int dense_z(int nobj) { return ND + 6 * nobj; }
+PG_HD constexpr int dense_rec(int nobj) { return 6 * dense_z(nobj) + 11; }        // 3 x (J, R) + invD[3] rhs[3] app[3] mu cfm-factor
+PG_HD constexpr int heavy_slots(int nobj) { return solver_slots(nobj) + (dense_supported(nobj) ? max_contacts(nobj) * dense_rec(nobj) : 0); }
+enum { SUB_OK = 0, SUB_REFUSED = 1, SUB_REFUSED_DIRTY = 2 };     // DIRTY: the caller's registers hold a half-done sub-step, reload the state
+
+// what the heavy solver needs from the sub-step's set-up (copied into local memory once: the solver is a real function call)
+template <typename T, int NOBJ> struct HeavyIO {
+    T Minv[ND][ND];
+    JointRows<T> R;
+    T qd[ND], max_imp[ND];
+    V3<T> O6, hy;
+    V3<T> opos[NOBJ > 0 ? NOBJ : 1], olin[NOBJ > 0 ? NOBJ : 1], oang[NOBJ > 0 ? NOBJ : 1];
+    T Iinv[NOBJ > 0 ? NOBJ : 1][6], inv_mass[NOBJ > 0 ? NOBJ : 1];
+    T soft_erp, soft_cfm;
+    T z[ND + 6 * (NOBJ > 0 ? NOBJ : 1)];        // out: velocity change [dvq, dvl, dva]
+    int nc, fast;                               // in: contacts, start with the watched-limit sweep
+    int capped, any_limit;                      // out: ran all 50 sweeps; an arm limit row carries impulse after a full solve
+};
+
+template <typename T, int NOBJ>
+PG_NOINLINE
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+void heavy_solve(HeavyIO<T, NOBJ>& H, T* sbase, int sstride) {
+    constexpr int Z = dense_z(NOBJ), DREC = dense_rec(NOBJ), D0 = solver_slots(NOBJ);
+    Contacts<T> C; C.st.base = sbase; C.st.stride = sstride;
+    const int nc = H.nc;
+    T Minv[ND][ND];
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+#pragma unroll
+        for (int j = 0; j < ND; j++) Minv[i][j] = H.Minv[i][j];
+    }
+    // ---- dense rows
+    {
+        OpSpace<T> Op; Op.O6 = H.O6; Op.hy = H.hy;
+        for (int c = 0; c < nc; c++) {
+            ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
+            const T dist = C.f(c, C_RHS), mu = C.f(c, C_MU);
+            V3<T> t1, t2; plane_space(X.n, t1, t2);
+            const T erp = X.soft ? H.soft_erp : Consts<T>::erp, cfm = X.soft ? H.soft_cfm : T(0);
+            const int base = D0 + c * DREC;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                const V3<T> d = k == 0 ? X.n : (k == 1 ? t1 : t2);
+                T J[Z], Rr[Z], den = T(0), rel = T(0);
+#pragma unroll
+                for (int i = 0; i < Z; i++) { J[i] = T(0); Rr[i] = T(0); }
+                if (X.rb >= 0) {
+                    T w[8]; robot_wrench<T, NOBJ>(Op, X, d, w);
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        T t = T(0);
+#pragma unroll
+                        for (int a = 0; a < 6; a++) t += C.jx(j, a) * w[a];
+                        J[j] = t;
+                    }
+                    J[7] = w[6]; J[8] = w[7];
+#pragma unroll
+                    for (int i = 0; i < ND; i++) {
+                        T t = T(0);
+#pragma unroll
+                        for (int j = 0; j < ND; j++) t += Minv[i][j] * J[j];
+                        Rr[i] = t; den += J[i] * t; rel += J[i] * H.qd[i];
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < NOBJ; o++) {
+                    if (X.sgo[o] != T(0)) {
+                        const T sg = X.sgo[o];
+                        V3<T> r = X.P - H.opos[o], rxd = cross(r, d), wa = sym6_mul(H.Iinv[o], rxd);
+                        J[ND + 6 * o] = sg * d.x; J[ND + 6 * o + 1] = sg * d.y; J[ND + 6 * o + 2] = sg * d.z;
+                        J[ND + 6 * o + 3] = sg * rxd.x; J[ND + 6 * o + 4] = sg * rxd.y; J[ND + 6 * o + 5] = sg * rxd.z;
+                        Rr[ND + 6 * o] = sg * d.x * H.inv_mass[o]; Rr[ND + 6 * o + 1] = sg * d.y * H.inv_mass[o]; Rr[ND + 6 * o + 2] = sg * d.z * H.inv_mass[o];
+                        Rr[ND + 6 * o + 3] = sg * wa.x; Rr[ND + 6 * o + 4] = sg * wa.y; Rr[ND + 6 * o + 5] = sg * wa.z;
+                        den += H.inv_mass[o] + dot(rxd, wa);
+                        rel += sg * dot(d, H.olin[o] + cross(H.oang[o], r));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < Z; i++) { C.st.at(base + k * 2 * Z + i) = J[i]; C.st.at(base + k * 2 * Z + Z + i) = Rr[i]; }
+                T inv, rhs;
+                if (k == 0) {
+                    inv = T(1) / (den + cfm);
+                    T pen = dist + T(1e-5), poserr = T(0), velerr = -rel;
+                    if (pen > 0) velerr -= pen * Consts<T>::inv_dt; else poserr = -pen * erp * Consts<T>::inv_dt;
+                    rhs = (poserr + velerr) * inv;
+                    C.st.at(base + 6 * Z + 9) = mu; C.st.at(base + 6 * Z + 10) = X.soft ? H.soft_cfm * inv : T(0);
+                } else { inv = T(1) / den; rhs = -rel * inv; }
+                C.st.at(base + 6 * Z + k) = inv; C.st.at(base + 6 * Z + 3 + k) = rhs; C.st.at(base + 6 * Z + 6 + k) = T(0);
+            }
+        }
+    }
+    // ---- sweeps
+    JointRows<T> R = H.R;
+    T mx[ND];
+#pragma unroll
+    for (int d = 0; d < ND; d++) mx[d] = H.max_imp[d];
+    T z[Z];
+#pragma unroll
+    for (int i = 0; i < Z; i++) z[i] = T(0);
+    bool fast = H.fast != 0;
+    int it = 0;
+    for (; it < 50; it++) {
+        T res = T(0), watch = T(0);
+        if (fast) joint_rows_sweep<true>(mx, Minv, R, z, it, res, watch);
+        else joint_rows_sweep<false>(mx, Minv, R, z, it, res, watch);
+        if (fast && watch > T(0)) {         // a watched arm-limit row would engage: start over with every row real
+#ifdef PG_HOST_DEBUG
+            g_dbg_fallbacks++;
+#endif
+            fast = false;
+#pragma unroll
+            for (int i = 0; i < Z; i++) z[i] = T(0);
+#pragma unroll
+            for (int d = 0; d < ND; d++) { R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+            for (int c = 0; c < nc; c++) { const int b = D0 + c * DREC + 6 * Z + 6; C.st.at(b) = T(0); C.st.at(b + 1) = T(0); C.st.at(b + 2) = T(0); }
+            it = -1;
+            continue;
+        }
+        for (int c = 0; c < nc; c++) {      // contact normals
+            const int base = D0 + c * DREC, sc = base + 6 * Z;
+            T j0 = T(0), j1 = T(0), j2 = T(0);
+#pragma unroll
+            for (int i = 0; i < Z; i++) { const T t = C.st.at(base + i) * z[i]; if (i % 3 == 0) j0 += t; else if (i % 3 == 1) j1 += t; else j2 += t; }
+            const T app = C.st.at(sc + 6), inv = C.st.at(sc);
+            T di = C.st.at(sc + 3) - app * C.st.at(sc + 10) - ((j0 + j1) + j2) * inv;
+            di = fmax(di, -app);
+            C.st.at(sc + 6) = app + di;
+#pragma unroll
+            for (int i = 0; i < Z; i++) z[i] += C.st.at(base + Z + i) * di;
+            res = fmax(res, fabs(div_fast(di, inv)));
+        }
+        for (int c = 0; c < nc; c++) {      // friction cones
+            const int base = D0 + c * DREC, sc = base + 6 * Z;
+            const T napp = C.st.at(sc + 6);
+            if (napp <= T(0)) continue;
+            T p0 = T(0), p1 = T(0), q0 = T(0), q1 = T(0);
+#pragma unroll
+            for (int i = 0; i < Z; i++) {
+                const T a = C.st.at(base + 2 * Z + i) * z[i], b = C.st.at(base + 4 * Z + i) * z[i];
+                if (i & 1) { p1 += a; q1 += b; } else { p0 += a; q0 += b; }
+            }
+            const T a1 = C.st.at(sc + 7), a2 = C.st.at(sc + 8), i1 = C.st.at(sc + 1), i2 = C.st.at(sc + 2);
+            T s1 = a1 + C.st.at(sc + 4) - (p0 + p1) * i1, s2 = a2 + C.st.at(sc + 5) - (q0 + q1) * i2;
+            const T lim = C.st.at(sc + 9) * napp, len = sqrt(s1 * s1 + s2 * s2);
+            if (len > lim) { const T f = div_fast(lim, len); s1 *= f; s2 *= f; }
+            const T d1 = s1 - a1, d2 = s2 - a2;
+            C.st.at(sc + 7) = s1; C.st.at(sc + 8) = s2;
+#pragma unroll
+            for (int i = 0; i < Z; i++) z[i] += C.st.at(base + 3 * Z + i) * d1 + C.st.at(base + 5 * Z + i) * d2;
+            res = fmax(res, fmax(fabs(div_fast(d1, i1)), fabs(div_fast(d2, i2))));
+        }
+#ifdef PG_HOST_DEBUG
+        g_dbg_sweeps++;
+#endif
+        if (res * res <= T(1e-7)) break;
+    }
+#ifdef PG_HOST_DEBUG
+    g_dbg_solves++; g_dbg_contacts += nc;
+    if (g_dbg_ntrace < 4096) g_dbg_trace[g_dbg_ntrace++] = it | (nc << 8) | (1 << 16) | (1 << 24);     // bit 24: the heavy path
+#endif
+#pragma unroll
+    for (int i = 0; i < Z; i++) H.z[i] = z[i];
+    H.capped = it >= 49;
+    bool any = false;
+    if (!fast) {
+#pragma unroll
+        for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
+    }
+    H.any_limit = any; H.fast = fast;
+}
+
+// One 2 ms stepSimulation through the split scheme.  `flag_full` is the env's "an arm limit row carried impulse in its last full solve"
+// bit (it travels in the scheduling key between launches).  Returns SUB_OK, or a refusal when the sub-step needs the heavy path and the
+// launch cannot run it (heavy_ok == false): SUB_REFUSED leaves q / qd / ob untouched, SUB_REFUSED_DIRTY (a watched limit row tripped in
+// the middle of the light solve) leaves them half-updated -- the caller reloads the state it committed after the previous sub-step.
+template <typename T, int NOBJ>
+PG_HD int env_substep_split(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& flag_full, const bool heavy_ok,
+                            T* sbase, int sstride) {
+    static_assert(dense_supported(NOBJ), "the dense heavy path exists for scenes with at most one object");
+    T sn[7], cs[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) sincos_t(q[i], sn[i], cs[i]);
+    World<T, NOBJ> W;
+    world_robot(M, S, q, sn, cs, W);
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) W.Ro[o] = quat_rot(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw);
+    collect_contacts<T, NOBJ>(S, W, ob, C);
+    bool need_full = flag_full || arm_limit_violated(M, q);
+    bool heavy = C.nr > 0 || need_full;
+    if (heavy && !heavy_ok) { flag_full = need_full; return SUB_REFUSED; }
+    T Minv[ND][ND], qdd[ND];
+    robot_dynamics_sc(M, q, qd, sn, cs, Minv, qdd);
+#pragma unroll
+    for (int d = 0; d < ND; d++) qd[d] += qdd[d] * Consts<T>::dt;
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) { obj_unconstrained(S, o, ob[o], W.Ro[o]); world_inertia(S, o, W); }
+    JointRows<T> R;
+    joint_rows_setup<true, false>(M, q, qd, target, Minv, R);
+    T dvq[ND];
+    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
+#pragma unroll
+    for (int d = 0; d < ND; d++) dvq[d] = T(0);
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+#ifdef PG_HOST_DEBUG
+    if (need_full) g_dbg_full_starts++;
+#endif
+    if (!heavy) {
+        OpSpace<T> Op;
+        rows_setup<T, NOBJ, false>(S, W, Op, ob, C);
+        const bool live = pgs_solve<T, NOBJ, true, false>(M, S, W, Op, Minv, R, C, ob, false, dvq, dvl, dva);
+        if (live) {     // a watched arm-limit row would have engaged: this sub-step belongs to the heavy path, every row real
+#ifdef PG_HOST_DEBUG
+            g_dbg_fallbacks++;
+#endif
+            flag_full = true;
+            if (!heavy_ok) return SUB_REFUSED_DIRTY;
+            heavy = true; need_full = true;
+#pragma unroll
+            for (int d = 0; d < ND; d++) { R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+            { const int dropped = C.dropped; collect_contacts<T, NOBJ>(S, W, ob, C); C.dropped = dropped; }   // the light row set-up consumed the parked distances: same poses, same records
+        } else flag_full = false;
+    }
+    if (heavy) {
+        HeavyIO<T, NOBJ> H;
+        {   // operational-space Jacobian of the gripper into the store (the dense rows are built from it), set-up data into H
+            const V3<T> O6 = W.F[6].p;
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                V3<T> zj = W.F[j].Z, l = cross(zj, O6 - W.F[j].p);
+                C.jx(j, 0) = zj.x; C.jx(j, 1) = zj.y; C.jx(j, 2) = zj.z; C.jx(j, 3) = l.x; C.jx(j, 4) = l.y; C.jx(j, 5) = l.z;
+            }
+            H.O6 = O6; H.hy = (W.F[6].X + W.F[6].Y) * Consts<T>::k45;
+#pragma unroll
+            for (int i = 0; i < ND; i++) {
+#pragma unroll
+                for (int j = 0; j < ND; j++) H.Minv[i][j] = Minv[i][j];
+                H.qd[i] = qd[i]; H.max_imp[i] = M.max_imp[i];
+            }
+            H.R = R;
+#pragma unroll
+            for (int o = 0; o < NOBJ; o++) {
+                H.opos[o] = ob[o].pos; H.olin[o] = ob[o].lin; H.oang[o] = ob[o].ang; H.inv_mass[o] = T(1) / S.mass[o];
+#pragma unroll
+                for (int k = 0; k < 6; k++) H.Iinv[o][k] = W.Iinv[o][k];
+            }
+            H.soft_erp = S.soft_erp; H.soft_cfm = S.soft_cfm; H.nc = C.n; H.fast = need_full ? 0 : 1;
+        }
+        heavy_solve<T, NOBJ>(H, sbase, sstride);
+#pragma unroll
+        for (int d = 0; d < ND; d++) dvq[d] = H.z[d];
+#pragma unroll
+        for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(H.z[ND + 6 * o], H.z[ND + 6 * o + 1], H.z[ND + 6 * o + 2]); dva[o] = mk<T>(H.z[ND + 6 * o + 3], H.z[ND + 6 * o + 4], H.z[ND + 6 * o + 5]); }
+        C.capped = H.capped != 0;
+        flag_full = H.any_limit != 0;
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) { ob[o].lin = ob[o].lin + dvl[o]; ob[o].ang = ob[o].ang + dva[o]; obj_integrate(ob[o]); }
+    return SUB_OK;
 }
 
 }  // namespace pg

@@ -212,9 +212,15 @@ template <int I, typename T> PG_HD void bwd_arm_link(const Model<T>& M, const T*
 
 // ---------------------------------------------------------------------------------------------- forward dynamics + M^-1
 // In: q, qd.  Out: qdd (unconstrained joint accelerations), Minv (dense symmetric 9x9), sn/cs of the arm joints.
+template <typename T> PG_HD void robot_dynamics_sc(const Model<T>& M, const T* q, const T* qd, const T* sn, const T* cs, T (*Minv)[ND], T* qdd);
 template <typename T> PG_HD void robot_dynamics(const Model<T>& M, const T* q, const T* qd, T* sn, T* cs, T (*Minv)[ND], T* qdd) {
 #pragma unroll
     for (int i = 0; i < 7; i++) sincos_t(q[i], sn[i], cs[i]);
+    robot_dynamics_sc(M, q, qd, sn, cs, Minv, qdd);
+}
+// the same with the arm joints' sines / cosines supplied by the caller (the split sub-step computes the world frames and collects the
+// contacts from them before it decides whether to run the dynamics at all)
+template <typename T> PG_HD void robot_dynamics_sc(const Model<T>& M, const T* q, const T* qd, const T* sn, const T* cs, T (*Minv)[ND], T* qdd) {
     SV<T> f[ND];
     RI<T> Ic[ND];
     {
@@ -633,8 +639,8 @@ template <int D, int FIRST, typename T> PG_HD void limit_pair(const T (*Minv)[ND
 #pragma unroll
     for (int k = 0; k < ND; k++) if (k != D) dv[k] += Minv[k][D] * w;
 }
-template <int D, typename T> PG_HD void motor_row(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
-    const T app = R.mot_app[D], mx = M.max_imp[D];
+template <int D, typename T> PG_HD void motor_row(const T* max_imp, const T (*Minv)[ND], JointRows<T>& R, T* dv, T& res) {
+    const T app = R.mot_app[D], mx = max_imp[D];
     const T di = fmin(fmax(R.mot_rhs[D] - dv[D] * R.invD[D], -mx - app), mx - app);     // |accumulated impulse| <= max force * dt, on the change
     R.mot_app[D] = app + di;
 #pragma unroll
@@ -657,11 +663,11 @@ template <int D, bool FAST, typename T> struct RowsFwd {
         if (FAST && D < 7) { limit_watch<D, 0>(R, dv, live); limit_watch<D, 1>(R, dv, live); }
         else limit_pair<D, 0>(Mi, R, dv, res);
     }
-    static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, FAST, T>::mot(M, Mi, R, dv, res); motor_row<D>(M, Mi, R, dv, res); }
+    static PG_HD void mot(const T* M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { RowsFwd<D - 1, FAST, T>::mot(M, Mi, R, dv, res); motor_row<D>(M, Mi, R, dv, res); }
 };
 template <bool FAST, typename T> struct RowsFwd<-1, FAST, T> {
     static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, T&) {}
-    static PG_HD void mot(const Model<T>&, const T (*)[ND], JointRows<T>&, T*, T&) {}
+    static PG_HD void mot(const T*, const T (*)[ND], JointRows<T>&, T*, T&) {}
 };
 template <int D, bool FAST, typename T> struct RowsRev {
     static PG_HD void lim(const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res, T& live) {
@@ -669,18 +675,21 @@ template <int D, bool FAST, typename T> struct RowsRev {
         else limit_pair<D, 1>(Mi, R, dv, res);
         RowsRev<D - 1, FAST, T>::lim(Mi, R, dv, res, live);
     }
-    static PG_HD void mot(const Model<T>& M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { motor_row<D>(M, Mi, R, dv, res); RowsRev<D - 1, FAST, T>::mot(M, Mi, R, dv, res); }
+    static PG_HD void mot(const T* M, const T (*Mi)[ND], JointRows<T>& R, T* dv, T& res) { motor_row<D>(M, Mi, R, dv, res); RowsRev<D - 1, FAST, T>::mot(M, Mi, R, dv, res); }
 };
 template <bool FAST, typename T> struct RowsRev<-1, FAST, T> {
     static PG_HD void lim(const T (*)[ND], JointRows<T>&, T*, T&, T&) {}
-    static PG_HD void mot(const Model<T>&, const T (*)[ND], JointRows<T>&, T*, T&) {}
+    static PG_HD void mot(const T*, const T (*)[ND], JointRows<T>&, T*, T&) {}
 };
 // one sweep over the non-contact rows; Bullet alternates the direction with the iteration parity.  `res` accumulates the largest
 // |velocity change| of the sweep (the exit test squares it: max of squares == square of the max magnitude, rounding is monotone);
 // `watch` > 0 afterwards means a watched arm-limit row would have engaged.
+template <bool FAST, typename T> PG_HD void joint_rows_sweep(const T* max_imp, const T (*Minv)[ND], JointRows<T>& R, T* dv, int it, T& res, T& live) {
+    if (it & 1) { RowsFwd<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); RowsFwd<ND - 1, FAST, T>::mot(max_imp, Minv, R, dv, res); }
+    else { RowsRev<ND - 1, FAST, T>::mot(max_imp, Minv, R, dv, res); RowsRev<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); }
+}
 template <bool FAST, typename T> PG_HD void joint_rows_sweep(const Model<T>& M, const T (*Minv)[ND], JointRows<T>& R, T* dv, int it, T& res, T& live) {
-    if (it & 1) { RowsFwd<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); RowsFwd<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); }
-    else { RowsRev<ND - 1, FAST, T>::mot(M, Minv, R, dv, res); RowsRev<ND - 1, FAST, T>::lim(Minv, R, dv, res, live); }
+    joint_rows_sweep<FAST>(M.max_imp, Minv, R, dv, it, res, live);
 }
 // true when an arm joint sits on or beyond a limit at set-up: its row is live from the start, use the full sweep
 template <typename T> PG_HD bool arm_limit_violated(const Model<T>& M, const T* q) {
