@@ -72,10 +72,6 @@ struct pg_env {
     // one group's launch (a few contact-heavy blocks) overlaps with the other groups' launches instead of idling the GPU
     long long* dbg = nullptr;
     int groups = 1; cudaStream_t gstream[8] = {}; cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
-    // split scheme (scenes with at most one object, sorted batches): every segment of a group is a light launch over the envs whose key says
-    // "no robot contact, limits slack", a heavy launch (151 kB of shared memory per 32 envs) over the others and a heavy launch over the envs
-    // the light one refused; PG_SPLIT=0 runs everything through heavy-capable launches, PG_HEAVY_STREAM=1 puts the heavy launch on its own stream
-    bool split = true; int heavy_stream = 0; cudaStream_t hvstream[8] = {}; cudaEvent_t ev_sorted[8] = {}, ev_heavy[8] = {};
     int segments = 4;                                 // launches per step for sorted batches (see pg_create); PG_SEGMENTS overrides (a divisor of 20)
     // host-buffer path: pinned staging + device I/O buffers + private stream
     cudaStream_t hstream = nullptr;
@@ -96,7 +92,6 @@ template <typename T> static void bind(EnvDev<T>& E, pg_env* e, char* base, unsi
     E.steps = (int*)take(n * sizeof(int)); E.episode = (unsigned*)take(n * sizeof(unsigned)); E.ret = (float*)take(n * sizeof(float));
     E.ccount = (unsigned short*)take(n * sizeof(unsigned short)); E.perm = (int*)take(n * sizeof(int));
     E.hist = (int*)take(((n + PERM_CHUNK - 1) / PERM_CHUNK + 8) * PERM_BUCKETS * sizeof(int));
-    E.sub = (int*)take(n * sizeof(int)); E.split = (int*)take(8 * sizeof(int)); E.rcount = (int*)take(8 * sizeof(int)); E.rlist = (int*)take(n * sizeof(int));
     e->blob_bytes = off;
 }
 
@@ -197,9 +192,6 @@ int pg_create(int task, int control_type, int reward_type, int num_envs, int dev
         for (int g = 0; g < e->groups; g++) { PG_CUDA(cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking)); PG_CUDA(cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming)); }
     }
     { const char* v = getenv("PG_SEGMENTS"); if (v) { int k = atoi(v); if (k >= 1 && k <= 20 && 20 % k == 0) e->segments = k; } }
-    e->split = dense_supported(e->nobj);
-    { const char* v = getenv("PG_SPLIT"); if (v && v[0] == '0') e->split = false; }
-    { const char* v = getenv("PG_HEAVY_STREAM"); if (v) e->heavy_stream = atoi(v); }
     *out = e;
     rc = pg_reset(e, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc != PG_OK) { pg_destroy(e); *out = nullptr; return rc; }
@@ -271,7 +263,6 @@ int pg_destroy(pg_env* e) {
     if (e->d_out) cudaFree(e->d_out);
     if (e->hstream) cudaStreamDestroy(e->hstream);
     for (int g = 0; g < 8; g++) { if (e->gstream[g]) cudaStreamDestroy(e->gstream[g]); if (e->ev_join[g]) cudaEventDestroy(e->ev_join[g]); }
-    for (int g = 0; g < 8; g++) { if (e->hvstream[g]) cudaStreamDestroy(e->hvstream[g]); if (e->ev_sorted[g]) cudaEventDestroy(e->ev_sorted[g]); if (e->ev_heavy[g]) cudaEventDestroy(e->ev_heavy[g]); }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->dbg) cudaFree(e->dbg);
     if (e->prims) cudaFree(e->prims);
@@ -333,16 +324,7 @@ int pg_set_substeps(pg_env* e, int n_substeps) {
 struct HostIO { const float* act; float* obs; float* ag; float* dg; float* rew; unsigned char* term; unsigned char* trunc; };
 static int ensure_group_streams(pg_env* e, int k) {
     if (!e->ev_fork) PG_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    if (e->heavy_stream) {
-        int lo = 0, hi = 0; PG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        for (int g = 0; g < (k > 1 ? k : 1); g++) {
-            if (!e->hvstream[g]) PG_CUDA(cudaStreamCreateWithPriority(&e->hvstream[g], cudaStreamNonBlocking, e->heavy_stream > 1 ? hi : lo));
-            if (!e->ev_sorted[g]) PG_CUDA(cudaEventCreateWithFlags(&e->ev_sorted[g], cudaEventDisableTiming));
-            if (!e->ev_heavy[g]) PG_CUDA(cudaEventCreateWithFlags(&e->ev_heavy[g], cudaEventDisableTiming));
-        }
-    }
     for (int g = 0; g < k; g++) {
-        if (k == 1) break;
         if (!e->gstream[g]) PG_CUDA(cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking));
         if (!e->ev_join[g]) PG_CUDA(cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming));
     }
@@ -365,7 +347,7 @@ static int step_impl(pg_env* e, const float* actions, const float* target_quat, 
     // host mode pipelines the copies against the env groups the configuration already has; PG_HOST_GROUPS forces more (measured: on one
     // GPU the single-stream Reach-joints configuration loses 5 % when cut into 4 groups only to overlap 0.2 ms of copies)
     if (hio && use_perm && e->n >= 16384) { static const int hg = getenv("PG_HOST_GROUPS") ? atoi(getenv("PG_HOST_GROUPS")) : 0; if (hg > groups && hg <= 8) groups = hg; }
-    if (groups > 1 || (use_perm && e->split && e->heavy_stream)) { int rc = ensure_group_streams(e, groups); if (rc != PG_OK) return rc; }
+    if (groups > 1) { int rc = ensure_group_streams(e, groups); if (rc != PG_OK) return rc; }
     // group g owns the envs (and thread slots) [g * gsize, min(n, (g + 1) * gsize)), gsize a multiple of the sort chunk
     const int gsize = ((e->n + groups - 1) / groups + PERM_CHUNK - 1) / PERM_CHUNK * PERM_CHUNK;
     const size_t A = e->act_dim, O = e->obs_dim, G = e->goal_dim;
@@ -380,33 +362,15 @@ static int step_impl(pg_env* e, const float* actions, const float* target_quat, 
         const int nchunks = (cnt + PERM_CHUNK - 1) / PERM_CHUNK;
         int* ghist = hist + (size_t)(t0 / PERM_CHUNK + g) * PERM_BUCKETS;
         const int nsub = e->Ef.P.nsub;
-        const bool split = use_perm && e->split;
-        int* dsplit = (e->precision == PG_F32 ? e->Ef.split : e->Ed.split) + g;
-        int* drcount = (e->precision == PG_F32 ? e->Ef.rcount : e->Ed.rcount) + g;
-        auto launch = [&](const StepIO& io, cudaStream_t s) {
-            if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, s); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, s);
-        };
         for (int sg = 0; sg < segs; sg++) {
-            StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset, sg * nsub / segs, (sg + 1) * nsub / segs, MODE_ALL, g, 1};
+            StepIO io{target_quat, actions, obs, ag, dg, reward, terminated, truncated, auto_reset, sg * nsub / segs, (sg + 1) * nsub / segs};
             if (io.s0 == io.s1) continue;       // fewer sub-steps than segments
             if (use_perm) {
                 perm_hist_kernel<<<nchunks, PERM_THREADS, 0, st>>>(key + t0, ghist, cnt);
-                perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, st>>>(key + t0, ghist, perm + t0, cnt, nchunks, t0, split ? dsplit : nullptr, split ? drcount : nullptr);
+                perm_scatter_kernel<<<nchunks, PERM_THREADS, 0, st>>>(key + t0, ghist, perm + t0, cnt, nchunks, t0);
                 g_launches += 2;
             }
-            if (!split) { launch(io, st); continue; }
-            // light launch || heavy launch, then the envs the light launch refused (their sub-step turned out to need the heavy path)
-            StepIO heavy = io; heavy.mode = MODE_HEAVY;
-            StepIO light = io; light.mode = MODE_LIGHT; light.heavy_ok = 0;
-            StepIO refused = io; refused.mode = MODE_REFUSED; if (refused.s0 == 0) refused.s0 = -1;   // not the step's first launch for its envs: their targets exist
-            if (e->heavy_stream) {
-                PG_CUDA(cudaEventRecord(e->ev_sorted[g], st)); PG_CUDA(cudaStreamWaitEvent(e->hvstream[g], e->ev_sorted[g], 0));
-                launch(heavy, e->hvstream[g]);
-                PG_CUDA(cudaEventRecord(e->ev_heavy[g], e->hvstream[g]));
-                launch(light, st);
-                PG_CUDA(cudaStreamWaitEvent(st, e->ev_heavy[g], 0));
-            } else { launch(heavy, st); launch(light, st); }
-            launch(refused, st);
+            if (e->precision == PG_F32) Dispatch<float>::step(e->task, Ef, e->ctrl, io, st); else Dispatch<double>::step(e->task, Ed, e->ctrl, io, st);
         }
         if (hio) {
             if (hio->obs) PG_CUDA(cudaMemcpyAsync(hio->obs + t0 * O, obs + t0 * O, (size_t)cnt * O * sizeof(float), cudaMemcpyDeviceToHost, st));

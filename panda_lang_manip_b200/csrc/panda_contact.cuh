@@ -253,7 +253,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
 
 // operational space of the gripper: Jx into the store, Lambda = Jx M^-1 Jx^T and v = Jx qd into registers
 template <typename T, int NOBJ>
-PG_HD void opspace_setup(const World<T, NOBJ>& W, const T (*Minv)[ND], const T* qd, Contacts<T>& C, OpSpace<T>& Op) {
+PG_HD void opspace_jx(const World<T, NOBJ>& W, Contacts<T>& C, OpSpace<T>& Op) {
     Op.O6 = W.F[6].p;
     Op.hy = (W.F[6].X + W.F[6].Y) * Consts<T>::k45;
 #pragma unroll
@@ -261,6 +261,8 @@ PG_HD void opspace_setup(const World<T, NOBJ>& W, const T (*Minv)[ND], const T* 
         V3<T> z = W.F[j].Z, l = cross(z, Op.O6 - W.F[j].p);
         C.jx(j, 0) = z.x; C.jx(j, 1) = z.y; C.jx(j, 2) = z.z; C.jx(j, 3) = l.x; C.jx(j, 4) = l.y; C.jx(j, 5) = l.z;
     }
+}
+template <typename T> PG_HD void opspace_lambda(const T (*Minv)[ND], const T* qd, Contacts<T>& C, OpSpace<T>& Op) {
 #pragma unroll
     for (int a = 0; a < 6; a++) {
         T row[7], Y[ND], va = T(0);
@@ -285,6 +287,11 @@ PG_HD void opspace_setup(const World<T, NOBJ>& W, const T (*Minv)[ND], const T* 
     }
     Op.L[sidx(6, 6)] = Minv[7][7]; Op.L[sidx(6, 7)] = Minv[7][8]; Op.L[sidx(7, 7)] = Minv[8][8];
     Op.v[6] = qd[7]; Op.v[7] = qd[8];
+}
+template <typename T, int NOBJ>
+PG_HD void opspace_setup(const World<T, NOBJ>& W, const T (*Minv)[ND], const T* qd, Contacts<T>& C, OpSpace<T>& Op) {
+    opspace_jx<T, NOBJ>(W, C, Op);
+    opspace_lambda<T>(Minv, qd, C, Op);
 }
 
 // per-contact decode shared by its three rows
@@ -469,14 +476,14 @@ PG_HD void contact_apply(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpa
 // ROBOT = false (the light path of the split scheme below): no robot box is in contact, so the operational-space code, the robot-on-table
 // rows and (with one object) the generic rows do not exist in the instantiation -- the contacts are object vertices on a plane only.
 template <typename T, int NOBJ, bool FAST, bool ROBOT = true>
-PG_HD bool pgs_solve(const Model<T>& M, const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const T (*Minv)[ND], JointRows<T>& R,
+PG_HD bool pgs_solve(const T* max_imp, const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<T>& Op, const T (*Minv)[ND], JointRows<T>& R,
                      Contacts<T>& C, const Obj<T>* ob, const bool robot_contacts, T* dvq, V3<T>* dvl, V3<T>* dva) {
     const int nc = C.n;
     bool live = false;
     int it = 0;
     for (; it < 50; it++) {
         T res = T(0), watch = T(0);
-        joint_rows_sweep<FAST>(M, Minv, R, dvq, it, res, watch);
+        joint_rows_sweep<FAST>(max_imp, Minv, R, dvq, it, res, watch);
         if (FAST && watch > T(0)) { live = true; break; }
         if ((ROBOT || NOBJ > 0) && nc > 0) {
             T d8[8], F8[8];
@@ -681,7 +688,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
     if (!fast) g_dbg_full_starts++;
 #endif
     bool live = false;
-    if (fast) live = pgs_solve<T, NOBJ, true>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+    if (fast) live = pgs_solve<T, NOBJ, true>(M.max_imp, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
     if (!fast || live) {
         full_sweep = true;
         if (live) {
@@ -694,7 +701,7 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
             for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
             for (int c = 0; c < nc; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
         }
-        pgs_solve<T, NOBJ, false>(M, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+        pgs_solve<T, NOBJ, false>(M.max_imp, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
         bool any = false;       // did an arm limit row actually carry impulse?  (decides whether the next step starts with the full sweep)
 #pragma unroll
         for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
@@ -707,209 +714,110 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
 }
 
 
-// ---------------------------------------------------------------------------------------------- split sub-step: light path / heavy path
+// ---------------------------------------------------------------------------------------------- task sub-step: light path inline, robot path out of line
 // Scenes with at most one object run every sub-step through one of two paths, chosen by the env's own state (never by the batch or the
 // schedule, so results do not depend on how a batch is launched):
 //
-//   light  no robot collision box is in contact and the arm joint limits are slack: the watched-limit sweep plus object-on-plane rows in
-//          the compact operational-space records (pgs_solve<FAST, ROBOT = false>), 17 words of shared memory per contact;
-//   heavy  a robot box touches the table or the object, or an arm limit is engaged: every contact row is set up once per sub-step as a
-//          DENSE row of the constraint Jacobian in the coordinates z = [joint velocities (9), object twist (6)] together with its
-//          impulse response W J^T (heavy_solve).  A row's sweep is then two dot-product-sized loops over shared memory (J z, z += R di)
-//          -- the same code for every contact kind, no operational-space products, no fold-back, no kind divergence inside a warp.
-//          101 words per contact with one object: a launch that may run it gives a 32-env block 151 kB of shared memory.
+//   light  no robot collision box is in contact and the arm joint limits are slack: the watched-limit sweep plus object-on-plane rows
+//          (pgs_solve<FAST, ROBOT = false>) -- the only solver loop that is inlined into the step kernel, ~1/3 of the code of the full one;
+//   robot  a robot box touches the table or the object, or an arm limit is engaged (or a watched row trips): the full operational-space
+//          solver (robot-on-table rows, generic rows, both sweep variants) in a separate, NON-INLINED function with its own register
+//          allocation.  What it needs from the sub-step's set-up is handed over in a local-memory record (~1 kB: the call happens
+//          once per sub-step, the copies are noise next to 50 sweeps), the contact records and Jx already sit in shared memory.
 //
-// A launch that does not own that much shared memory (the "light" launches of a sorted batch) REFUSES a heavy sub-step before it touches
-// the state; the host side then runs the env in a heavy launch.  The heavy path is a separate, non-inlined function: the light path's
-// register allocation and instruction footprint do not see it.
+// Round 1 inlined both sweep variants and all contact kinds into one kernel body: with ee control the second instantiation cost 13-25 %
+// (code size, register allocation of the hot loop), which is why ee control ran the full sweep for everybody.  Out of line, every
+// configuration gets the watched sweep on its light path.
+// (A dense variant of the robot path -- every contact row as a dense Jacobian row + impulse response in [joint velocities, object
+// twist], 101 words per contact -- was built and measured in round 2: same results, 3x shorter worst-case sub-step for PickAndPlace, but
+// its 151 kB per 32 envs leave one such warp per SM and the step got slower; profiles/r2_split_experiment)
 #ifdef __CUDACC__
 #define PG_NOINLINE __noinline__
 #else
 #define PG_NOINLINE __attribute__((noinline))
 #endif
-PG_HD constexpr bool dense_supported(int nobj) { return nobj <= 1; }
-PG_HD constexpr int dense_z(int nobj) { return ND + 6 * nobj; }
-PG_HD constexpr int dense_rec(int nobj) { return 6 * dense_z(nobj) + 11; }        // 3 x (J, R) + invD[3] rhs[3] app[3] mu cfm-factor
-PG_HD constexpr int heavy_slots(int nobj) { return solver_slots(nobj) + (dense_supported(nobj) ? max_contacts(nobj) * dense_rec(nobj) : 0); }
-enum { SUB_OK = 0, SUB_REFUSED = 1, SUB_REFUSED_DIRTY = 2 };     // DIRTY: the caller's registers hold a half-done sub-step, reload the state
+PG_HD constexpr bool split_supported(int nobj) { return nobj <= 1; }
 
-// what the heavy solver needs from the sub-step's set-up (copied into local memory once: the solver is a real function call)
-template <typename T, int NOBJ> struct HeavyIO {
+template <typename T, int NOBJ> struct RobotIO {
     T Minv[ND][ND];
     JointRows<T> R;
     T qd[ND], max_imp[ND];
     V3<T> O6, hy;
-    V3<T> opos[NOBJ > 0 ? NOBJ : 1], olin[NOBJ > 0 ? NOBJ : 1], oang[NOBJ > 0 ? NOBJ : 1];
-    T Iinv[NOBJ > 0 ? NOBJ : 1][6], inv_mass[NOBJ > 0 ? NOBJ : 1];
-    T soft_erp, soft_cfm;
+    Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+    T Iinv[NOBJ > 0 ? NOBJ : 1][6];
     T z[ND + 6 * (NOBJ > 0 ? NOBJ : 1)];        // out: velocity change [dvq, dvl, dva]
-    int nc, fast;                               // in: contacts, start with the watched-limit sweep
+    int n, nr, nB, nA, fast;                    // in: contact counters of the collection, start with the watched-limit sweep
     int capped, any_limit;                      // out: ran all 50 sweeps; an arm limit row carries impulse after a full solve
 };
 
-template <typename T, int NOBJ>
+template <typename T, int NOBJ, int STRIDE>
 PG_NOINLINE
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-void heavy_solve(HeavyIO<T, NOBJ>& H, T* sbase, int sstride) {
-    constexpr int Z = dense_z(NOBJ), DREC = dense_rec(NOBJ), D0 = solver_slots(NOBJ);
-    Contacts<T> C; C.st.base = sbase; C.st.stride = sstride;
-    const int nc = H.nc;
-    T Minv[ND][ND];
+void robot_solve(const Scene<T>& S, RobotIO<T, NOBJ>& H, T* sbase) {
+    Contacts<T> C; C.st.base = sbase; C.st.stride = STRIDE;
+    C.n = H.n; C.nr = H.nr; C.nB = H.nB; C.nA = H.nA; C.cap = max_contacts(NOBJ); C.dropped = 0; C.near = false; C.capped = false;
+    T Minv[ND][ND], qd[ND], mx[ND];
 #pragma unroll
     for (int i = 0; i < ND; i++) {
 #pragma unroll
         for (int j = 0; j < ND; j++) Minv[i][j] = H.Minv[i][j];
+        qd[i] = H.qd[i]; mx[i] = H.max_imp[i];
     }
-    // ---- dense rows
-    {
-        OpSpace<T> Op; Op.O6 = H.O6; Op.hy = H.hy;
-        for (int c = 0; c < nc; c++) {
-            ContactCtx<T, NOBJ> X = contact_ctx<T, NOBJ>(C, c);
-            const T dist = C.f(c, C_RHS), mu = C.f(c, C_MU);
-            V3<T> t1, t2; plane_space(X.n, t1, t2);
-            const T erp = X.soft ? H.soft_erp : Consts<T>::erp, cfm = X.soft ? H.soft_cfm : T(0);
-            const int base = D0 + c * DREC;
-#pragma unroll 1
-            for (int k = 0; k < 3; k++) {
-                const V3<T> d = k == 0 ? X.n : (k == 1 ? t1 : t2);
-                T J[Z], Rr[Z], den = T(0), rel = T(0);
+    OpSpace<T> Op; Op.O6 = H.O6; Op.hy = H.hy;
+    const bool robot_contacts = H.nr > 0;
+    if (robot_contacts) opspace_lambda<T>(Minv, qd, C, Op);
+    World<T, NOBJ> W;
+    Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
 #pragma unroll
-                for (int i = 0; i < Z; i++) { J[i] = T(0); Rr[i] = T(0); }
-                if (X.rb >= 0) {
-                    T w[8]; robot_wrench<T, NOBJ>(Op, X, d, w);
+    for (int o = 0; o < NOBJ; o++) {
+        ob[o] = H.ob[o];
 #pragma unroll
-                    for (int j = 0; j < 7; j++) {
-                        T t = T(0);
-#pragma unroll
-                        for (int a = 0; a < 6; a++) t += C.jx(j, a) * w[a];
-                        J[j] = t;
-                    }
-                    J[7] = w[6]; J[8] = w[7];
-#pragma unroll
-                    for (int i = 0; i < ND; i++) {
-                        T t = T(0);
-#pragma unroll
-                        for (int j = 0; j < ND; j++) t += Minv[i][j] * J[j];
-                        Rr[i] = t; den += J[i] * t; rel += J[i] * H.qd[i];
-                    }
-                }
-#pragma unroll
-                for (int o = 0; o < NOBJ; o++) {
-                    if (X.sgo[o] != T(0)) {
-                        const T sg = X.sgo[o];
-                        V3<T> r = X.P - H.opos[o], rxd = cross(r, d), wa = sym6_mul(H.Iinv[o], rxd);
-                        J[ND + 6 * o] = sg * d.x; J[ND + 6 * o + 1] = sg * d.y; J[ND + 6 * o + 2] = sg * d.z;
-                        J[ND + 6 * o + 3] = sg * rxd.x; J[ND + 6 * o + 4] = sg * rxd.y; J[ND + 6 * o + 5] = sg * rxd.z;
-                        Rr[ND + 6 * o] = sg * d.x * H.inv_mass[o]; Rr[ND + 6 * o + 1] = sg * d.y * H.inv_mass[o]; Rr[ND + 6 * o + 2] = sg * d.z * H.inv_mass[o];
-                        Rr[ND + 6 * o + 3] = sg * wa.x; Rr[ND + 6 * o + 4] = sg * wa.y; Rr[ND + 6 * o + 5] = sg * wa.z;
-                        den += H.inv_mass[o] + dot(rxd, wa);
-                        rel += sg * dot(d, H.olin[o] + cross(H.oang[o], r));
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < Z; i++) { C.st.at(base + k * 2 * Z + i) = J[i]; C.st.at(base + k * 2 * Z + Z + i) = Rr[i]; }
-                T inv, rhs;
-                if (k == 0) {
-                    inv = T(1) / (den + cfm);
-                    T pen = dist + T(1e-5), poserr = T(0), velerr = -rel;
-                    if (pen > 0) velerr -= pen * Consts<T>::inv_dt; else poserr = -pen * erp * Consts<T>::inv_dt;
-                    rhs = (poserr + velerr) * inv;
-                    C.st.at(base + 6 * Z + 9) = mu; C.st.at(base + 6 * Z + 10) = X.soft ? H.soft_cfm * inv : T(0);
-                } else { inv = T(1) / den; rhs = -rel * inv; }
-                C.st.at(base + 6 * Z + k) = inv; C.st.at(base + 6 * Z + 3 + k) = rhs; C.st.at(base + 6 * Z + 6 + k) = T(0);
-            }
-        }
+        for (int k = 0; k < 6; k++) W.Iinv[o][k] = H.Iinv[o][k];
     }
-    // ---- sweeps
+    rows_setup<T, NOBJ, true>(S, W, Op, ob, C);
     JointRows<T> R = H.R;
-    T mx[ND];
+    T dvq[ND];
+    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
 #pragma unroll
-    for (int d = 0; d < ND; d++) mx[d] = H.max_imp[d];
-    T z[Z];
+    for (int d = 0; d < ND; d++) dvq[d] = T(0);
 #pragma unroll
-    for (int i = 0; i < Z; i++) z[i] = T(0);
-    bool fast = H.fast != 0;
-    int it = 0;
-    for (; it < 50; it++) {
-        T res = T(0), watch = T(0);
-        if (fast) joint_rows_sweep<true>(mx, Minv, R, z, it, res, watch);
-        else joint_rows_sweep<false>(mx, Minv, R, z, it, res, watch);
-        if (fast && watch > T(0)) {         // a watched arm-limit row would engage: start over with every row real
+    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+    const bool fast = H.fast != 0;
+    bool live = false, any = false;
+    if (fast) live = pgs_solve<T, NOBJ, true, true>(mx, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+    if (!fast || live) {
+        if (live) {
 #ifdef PG_HOST_DEBUG
             g_dbg_fallbacks++;
 #endif
-            fast = false;
 #pragma unroll
-            for (int i = 0; i < Z; i++) z[i] = T(0);
+            for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
 #pragma unroll
-            for (int d = 0; d < ND; d++) { R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
-            for (int c = 0; c < nc; c++) { const int b = D0 + c * DREC + 6 * Z + 6; C.st.at(b) = T(0); C.st.at(b + 1) = T(0); C.st.at(b + 2) = T(0); }
-            it = -1;
-            continue;
+            for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+            for (int c = 0; c < C.n; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
         }
-        for (int c = 0; c < nc; c++) {      // contact normals
-            const int base = D0 + c * DREC, sc = base + 6 * Z;
-            T j0 = T(0), j1 = T(0), j2 = T(0);
-#pragma unroll
-            for (int i = 0; i < Z; i++) { const T t = C.st.at(base + i) * z[i]; if (i % 3 == 0) j0 += t; else if (i % 3 == 1) j1 += t; else j2 += t; }
-            const T app = C.st.at(sc + 6), inv = C.st.at(sc);
-            T di = C.st.at(sc + 3) - app * C.st.at(sc + 10) - ((j0 + j1) + j2) * inv;
-            di = fmax(di, -app);
-            C.st.at(sc + 6) = app + di;
-#pragma unroll
-            for (int i = 0; i < Z; i++) z[i] += C.st.at(base + Z + i) * di;
-            res = fmax(res, fabs(div_fast(di, inv)));
-        }
-        for (int c = 0; c < nc; c++) {      // friction cones
-            const int base = D0 + c * DREC, sc = base + 6 * Z;
-            const T napp = C.st.at(sc + 6);
-            if (napp <= T(0)) continue;
-            T p0 = T(0), p1 = T(0), q0 = T(0), q1 = T(0);
-#pragma unroll
-            for (int i = 0; i < Z; i++) {
-                const T a = C.st.at(base + 2 * Z + i) * z[i], b = C.st.at(base + 4 * Z + i) * z[i];
-                if (i & 1) { p1 += a; q1 += b; } else { p0 += a; q0 += b; }
-            }
-            const T a1 = C.st.at(sc + 7), a2 = C.st.at(sc + 8), i1 = C.st.at(sc + 1), i2 = C.st.at(sc + 2);
-            T s1 = a1 + C.st.at(sc + 4) - (p0 + p1) * i1, s2 = a2 + C.st.at(sc + 5) - (q0 + q1) * i2;
-            const T lim = C.st.at(sc + 9) * napp, len = sqrt(s1 * s1 + s2 * s2);
-            if (len > lim) { const T f = div_fast(lim, len); s1 *= f; s2 *= f; }
-            const T d1 = s1 - a1, d2 = s2 - a2;
-            C.st.at(sc + 7) = s1; C.st.at(sc + 8) = s2;
-#pragma unroll
-            for (int i = 0; i < Z; i++) z[i] += C.st.at(base + 3 * Z + i) * d1 + C.st.at(base + 5 * Z + i) * d2;
-            res = fmax(res, fmax(fabs(div_fast(d1, i1)), fabs(div_fast(d2, i2))));
-        }
-#ifdef PG_HOST_DEBUG
-        g_dbg_sweeps++;
-#endif
-        if (res * res <= T(1e-7)) break;
-    }
-#ifdef PG_HOST_DEBUG
-    g_dbg_solves++; g_dbg_contacts += nc;
-    if (g_dbg_ntrace < 4096) g_dbg_trace[g_dbg_ntrace++] = it | (nc << 8) | (1 << 16) | (1 << 24);     // bit 24: the heavy path
-#endif
-#pragma unroll
-    for (int i = 0; i < Z; i++) H.z[i] = z[i];
-    H.capped = it >= 49;
-    bool any = false;
-    if (!fast) {
+        pgs_solve<T, NOBJ, false, true>(mx, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
 #pragma unroll
         for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
     }
-    H.any_limit = any; H.fast = fast;
+#pragma unroll
+    for (int d = 0; d < ND; d++) H.z[d] = dvq[d];
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        H.z[ND + 6 * o] = dvl[o].x; H.z[ND + 6 * o + 1] = dvl[o].y; H.z[ND + 6 * o + 2] = dvl[o].z;
+        H.z[ND + 6 * o + 3] = dva[o].x; H.z[ND + 6 * o + 4] = dva[o].y; H.z[ND + 6 * o + 5] = dva[o].z;
+    }
+    H.capped = C.capped; H.any_limit = any;
 }
 
-// One 2 ms stepSimulation through the split scheme.  `flag_full` is the env's "an arm limit row carried impulse in its last full solve"
-// bit (it travels in the scheduling key between launches).  Returns SUB_OK, or a refusal when the sub-step needs the heavy path and the
-// launch cannot run it (heavy_ok == false): SUB_REFUSED leaves q / qd / ob untouched, SUB_REFUSED_DIRTY (a watched limit row tripped in
-// the middle of the light solve) leaves them half-updated -- the caller reloads the state it committed after the previous sub-step.
-template <typename T, int NOBJ>
-PG_HD int env_substep_split(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& flag_full, const bool heavy_ok,
-                            T* sbase, int sstride) {
-    static_assert(dense_supported(NOBJ), "the dense heavy path exists for scenes with at most one object");
+// One 2 ms stepSimulation of a task scene with at most one object.  `flag_full` is the env's "an arm limit row carried impulse in its
+// last full solve" bit (it travels in the scheduling key from sub-step to sub-step, a function of the env's own history).
+template <typename T, int NOBJ, int STRIDE>
+PG_HD void env_substep_task(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& flag_full) {
+    static_assert(split_supported(NOBJ), "two-object scenes run env_substep");
+    // contacts first (they depend on the poses only): the collection's registers are dead before the dynamics needs its own
     T sn[7], cs[7];
 #pragma unroll
     for (int i = 0; i < 7; i++) sincos_t(q[i], sn[i], cs[i]);
@@ -918,9 +826,6 @@ PG_HD int env_substep_split(const Model<T>& M, const Scene<T>& S, T* q, T* qd, c
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) W.Ro[o] = quat_rot(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw);
     collect_contacts<T, NOBJ>(S, W, ob, C);
-    bool need_full = flag_full || arm_limit_violated(M, q);
-    bool heavy = C.nr > 0 || need_full;
-    if (heavy && !heavy_ok) { flag_full = need_full; return SUB_REFUSED; }
     T Minv[ND][ND], qdd[ND];
     robot_dynamics_sc(M, q, qd, sn, cs, Minv, qdd);
 #pragma unroll
@@ -935,35 +840,31 @@ PG_HD int env_substep_split(const Model<T>& M, const Scene<T>& S, T* q, T* qd, c
     for (int d = 0; d < ND; d++) dvq[d] = T(0);
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+    bool need_full = flag_full || arm_limit_violated(M, q);
+    bool robot = C.nr > 0 || need_full;
 #ifdef PG_HOST_DEBUG
     if (need_full) g_dbg_full_starts++;
 #endif
-    if (!heavy) {
+    if (!robot) {
         OpSpace<T> Op;
         rows_setup<T, NOBJ, false>(S, W, Op, ob, C);
-        const bool live = pgs_solve<T, NOBJ, true, false>(M, S, W, Op, Minv, R, C, ob, false, dvq, dvl, dva);
-        if (live) {     // a watched arm-limit row would have engaged: this sub-step belongs to the heavy path, every row real
+        const bool live = pgs_solve<T, NOBJ, true, false>(M.max_imp, S, W, Op, Minv, R, C, ob, false, dvq, dvl, dva);
+        if (live) {     // a watched arm-limit row would have engaged: this sub-step belongs to the robot path, every row real, from zero impulses
 #ifdef PG_HOST_DEBUG
             g_dbg_fallbacks++;
 #endif
-            flag_full = true;
-            if (!heavy_ok) return SUB_REFUSED_DIRTY;
-            heavy = true; need_full = true;
+            robot = true; need_full = true;
 #pragma unroll
             for (int d = 0; d < ND; d++) { R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
             { const int dropped = C.dropped; collect_contacts<T, NOBJ>(S, W, ob, C); C.dropped = dropped; }   // the light row set-up consumed the parked distances: same poses, same records
         } else flag_full = false;
     }
-    if (heavy) {
-        HeavyIO<T, NOBJ> H;
-        {   // operational-space Jacobian of the gripper into the store (the dense rows are built from it), set-up data into H
-            const V3<T> O6 = W.F[6].p;
-#pragma unroll
-            for (int j = 0; j < 7; j++) {
-                V3<T> zj = W.F[j].Z, l = cross(zj, O6 - W.F[j].p);
-                C.jx(j, 0) = zj.x; C.jx(j, 1) = zj.y; C.jx(j, 2) = zj.z; C.jx(j, 3) = l.x; C.jx(j, 4) = l.y; C.jx(j, 5) = l.z;
-            }
-            H.O6 = O6; H.hy = (W.F[6].X + W.F[6].Y) * Consts<T>::k45;
+    if (robot) {
+        RobotIO<T, NOBJ> H;
+        {
+            OpSpace<T> Op;
+            opspace_jx<T, NOBJ>(W, C, Op);
+            H.O6 = Op.O6; H.hy = Op.hy;
 #pragma unroll
             for (int i = 0; i < ND; i++) {
 #pragma unroll
@@ -973,13 +874,13 @@ PG_HD int env_substep_split(const Model<T>& M, const Scene<T>& S, T* q, T* qd, c
             H.R = R;
 #pragma unroll
             for (int o = 0; o < NOBJ; o++) {
-                H.opos[o] = ob[o].pos; H.olin[o] = ob[o].lin; H.oang[o] = ob[o].ang; H.inv_mass[o] = T(1) / S.mass[o];
+                H.ob[o] = ob[o];
 #pragma unroll
                 for (int k = 0; k < 6; k++) H.Iinv[o][k] = W.Iinv[o][k];
             }
-            H.soft_erp = S.soft_erp; H.soft_cfm = S.soft_cfm; H.nc = C.n; H.fast = need_full ? 0 : 1;
+            H.n = C.n; H.nr = C.nr; H.nB = C.nB; H.nA = C.nA; H.fast = need_full ? 0 : 1;
         }
-        heavy_solve<T, NOBJ>(H, sbase, sstride);
+        robot_solve<T, NOBJ, STRIDE>(S, H, C.st.base);
 #pragma unroll
         for (int d = 0; d < ND; d++) dvq[d] = H.z[d];
 #pragma unroll
@@ -991,7 +892,6 @@ PG_HD int env_substep_split(const Model<T>& M, const Scene<T>& S, T* q, T* qd, c
     for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { ob[o].lin = ob[o].lin + dvl[o]; ob[o].ang = ob[o].ang + dva[o]; obj_integrate(ob[o]); }
-    return SUB_OK;
 }
 
 }  // namespace pg

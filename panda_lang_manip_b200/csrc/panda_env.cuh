@@ -192,45 +192,34 @@ PG_HD void step_reward(int reward_type, const float* ag, const double* goal, dou
     reward = reward_from_distance(reward_type, d, thr);
 }
 
-// The simulation part of RobotTaskEnv.step for one environment: sub-steps [s, s1) of it (a step may be cut into segments so that the envs
-// can be re-sorted in between; the motor targets travel through `target`).  q/qd/ob are updated in place; qc receives the link-transform
-// cache of the last sub-step (valid when the step's last sub-step ran here).  `s` is the env's own sub-step counter: in, where it stands;
-// out, where it stopped -- s1, or earlier when a launch without the heavy path's shared memory (heavy_ok == false) met a sub-step that
-// needs it (scenes with at most one object, see env_substep_split): the function then returns SUB_REFUSED with the state as it was at
-// the start of sub-step s.  `hooks.commit(s)` is called after every completed sub-step of such a launch (the state in the caller's arrays
-// is the state at the start of sub-step s) and `hooks.reload()` must bring that state back.
-struct NoHooks { PG_HD void commit(int) {} PG_HD void reload() {} };
-template <typename T, int TASK, int CTRL, typename Hooks>
-PG_HD int env_step_sim(const Model<T>& M, const Scene<T>& S, T* q, T* qd, Obj<T>* ob, const float* action, const float* target_quat, Contacts<T>& C, int& sched_key,
-                       T* target, T* qc, int& s, int s1, int nsub, bool have_target, bool heavy_ok, Hooks& hooks) {
+// The simulation part of RobotTaskEnv.step for one environment, or the sub-step range [s0, s1) of it (a step may be cut into segments so
+// that the envs can be re-sorted in between; the motor targets travel through `target`).  q/qd/ob are updated in place; qc receives the
+// link-transform cache of the last sub-step (valid when s1 == nsub).  STRIDE: word stride of the env's column in the contact store.
+template <typename T, int TASK, int CTRL, int STRIDE>
+PG_HD void env_step_sim(const Model<T>& M, const Scene<T>& S, T* q, T* qd, Obj<T>* ob, const float* action, const float* target_quat, Contacts<T>& C, int& sched_key,
+                        T* target, T* qc, int s0 = 0, int s1 = 20, int nsub = 20) {
     constexpr int NOBJ = task_nobj(TASK);
-    if (!have_target) env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
-    int nsub_contact = 0, status = SUB_OK; bool near = false;
-    if constexpr (dense_supported(NOBJ)) {
-        // split scheme: the env's "an arm limit carried impulse" bit travels in the key from sub-step to sub-step (a function of the env's
-        // own history, whatever the segmentation of the step)
+    if (s0 == 0) env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
+    int nsub_contact = 0; bool near = false;
+    if constexpr (split_supported(NOBJ)) {
+        // light path inline / robot path out of line (env_substep_task); the env's "an arm limit carried impulse" bit travels in the key from
+        // sub-step to sub-step: a function of the env's own history, whatever the segmentation of the step
         bool flag_full = (sched_key & KEY_FULL) != 0;
-        C.n = 0; C.nr = 0; C.nB = 0; C.nA = 0; C.near = false; C.capped = false;
-        for (; s < s1; s++) {
+        for (int s = s0; s < s1; s++) {
             if (s == nsub - 1) {
 #pragma unroll
                 for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
             }
-            status = env_substep_split<T, NOBJ>(M, S, q, qd, target, ob, C, flag_full, heavy_ok, C.st.base, C.st.stride);
-            if (status != SUB_OK) { if (status == SUB_REFUSED_DIRTY) hooks.reload(); status = SUB_REFUSED; break; }
+            env_substep_task<T, NOBJ, STRIDE>(M, S, q, qd, target, ob, C, flag_full);
             if (C.n > 0) nsub_contact++;
             near = near || C.near;
-            if (!heavy_ok && s + 1 < s1) hooks.commit(s + 1);
         }
-        const int ngen = C.n - C.nB - C.nA;
-        (void)ngen;
-        sched_key = (C.n < 31 ? C.n : 31) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0 || C.near) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (flag_full ? KEY_FULL : 0);
-        return status;
+        sched_key = (C.n < 31 ? C.n : 31) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (flag_full ? KEY_FULL : 0);
     } else {
-        // two-object scenes (and any scene through the legacy path): sticky full sweep -- once an arm limit engaged, later sub-steps of the launch
-        // (and, through the key's KEY_FULL bit, the next launch) start with the full sweep; dropped after a launch in which no arm limit row carried impulse
+        // two-object scenes: everything inline, sticky full sweep -- once an arm limit engaged, later sub-steps of the launch (and, through the
+        // key's KEY_FULL bit, the next launch) start with the full sweep; dropped after a launch in which no arm limit row carried impulse
         bool full_sweep = (sched_key & KEY_FULL) != 0, limits_active = false;
-        for (; s < s1; s++) {
+        for (int s = s0; s < s1; s++) {
             if (s == nsub - 1) {
 #pragma unroll
                 for (int d = 0; d < ND; d++) qc[d] = q[d];
@@ -245,7 +234,6 @@ PG_HD int env_step_sim(const Model<T>& M, const Scene<T>& S, T* q, T* qd, Obj<T>
         // scheduling key for the next launch (see perm_bucket): the contact picture of this launch's last sub-step
         const int ngen = C.n - C.nB - C.nA;                     // generic contacts (robot box <-> object, object <-> object): the most expensive rows
         sched_key = (C.n < 31 ? C.n : 31) | (NOBJ == 2 ? (ngen < 15 ? ngen : 15) << 10 : 0) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (limits_active ? KEY_FULL : 0);
-        return SUB_OK;
     }
 }
 // _get_obs + is_success + compute_reward of the step that just ended (core.py:283-288)
@@ -256,12 +244,11 @@ PG_HD void env_step_finish(const Model<T>& M, int reward_type, const T* q, const
     step_reward<TASK>(reward_type, ag, goal, thr, reward, success);
 }
 // the whole step (host test build and small callers)
-template <typename T, int TASK, int CTRL>
+template <typename T, int TASK, int CTRL, int STRIDE = 1>
 PG_HD void env_step(const Model<T>& M, const Scene<T>& S, int reward_type, T* q, T* qd, Obj<T>* ob, const double* goal, const float* action, const float* target_quat,
                     float* obs, float* ag, float* dg, float& reward, unsigned char& success, Contacts<T>& C, int& sched_key, T* target, int nsub = 20, double thr = -1.0) {
     T qc[ND];
-    int sub = 0; NoHooks hooks;
-    env_step_sim<T, TASK, CTRL>(M, S, q, qd, ob, action, target_quat, C, sched_key, target, qc, sub, nsub, nsub, false, true, hooks);
+    env_step_sim<T, TASK, CTRL, STRIDE>(M, S, q, qd, ob, action, target_quat, C, sched_key, target, qc, 0, nsub, nsub);
     env_step_finish<T, TASK>(M, reward_type, q, qd, qc, ob, goal, thr < 0.0 ? threshold_f64(TASK) : thr, obs, ag, dg, reward, success);
 }
 

@@ -10,6 +10,11 @@
 namespace pg {
 
 constexpr int BLOCK = 128;
+// envs per block of the step kernel (a block is what the SM schedules and frees: smaller blocks release their shared memory and warp
+// slots as soon as their own envs are done); A/B: make EXTRA=-DPG_STEP_BLOCK=32
+#ifndef PG_STEP_BLOCK
+#define PG_STEP_BLOCK 128
+#endif
 
 template <typename T> struct EnvDev {
     int n;                       // environments on this device
@@ -31,24 +36,15 @@ template <typename T> struct EnvDev {
     unsigned short* ccount;      // [n] scheduling key written by the env's last launch (see KEY_* in panda_env.cuh)
     long long* dbg;              // [n][2] per-thread-slot (cycles spent in env_step, key) of the last launch, or NULL (PG_DEBUG_TIMING=1)
     int* hist;                   // [ceil(n/1024)][24] scratch of the bucket sort
-    int* sub;                    // [n] where the env stands inside its step: -1 between steps, else the next sub-step (| SUB_TARGET once the motor targets are in `target`)
-    int* split;                  // [8] per env group: thread slots [0, split) of the sorted map hold the envs whose key asks for the heavy path
-    int* rcount;                 // [8] per env group: envs refused by the group's light launch (their sub-step needs the heavy path) ...
-    int* rlist;                  // [n] ... and their indices, group g's at [t0, t0 + rcount[g])
     Model<T> M;
     Scene<T> S;
     TaskParams P;
 };
-enum { SUB_TARGET = 1 << 30, SUB_MASK = SUB_TARGET - 1 };
-// which thread slots a launch covers: all of them, or one side of the light / heavy split of a sorted group, or the group's refused list
-enum { MODE_ALL = 0, MODE_LIGHT = 1, MODE_HEAVY = 2, MODE_REFUSED = 3 };
 struct StepIO {
     const float* target_quat;    // [n,4] (x,y,z,w) EE target orientation for ee control, or NULL = (1,0,0,0)
     const float* actions; float* obs; float* ag; float* dg; float* reward; unsigned char* terminated; unsigned char* truncated;
     int auto_reset;
-    int s0, s1;                  // this launch advances its envs to sub-step s1 (s0 == 0: the launch starts the step); [0, nsub) = a whole step
-    int mode, group;             // MODE_*, env group (index into split / rcount)
-    int heavy_ok;                // the launch owns the heavy path's shared memory (heavy_slots words per env); otherwise it refuses heavy sub-steps
+    int s0, s1;                  // sub-step range of this launch: [0, nsub) = a whole step
 };
 struct ResetIO {
     const unsigned char* mask; const double* goal_override; const double* object_override; float* obs; float* ag; float* dg;
@@ -214,7 +210,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ En
         store_state<T, NOBJ>(E, i, q, qd, ob);
 #pragma unroll
         for (int k = 0; k < 6; k++) E.goal[k * E.n + i] = goal[k];
-        E.steps[i] = 0; E.episode[i] = ep; E.ret[i] = 0.0f; E.ccount[i] = 0; E.sub[i] = -1;
+        E.steps[i] = 0; E.episode[i] = ep; E.ret[i] = 0.0f; E.ccount[i] = 0;
         env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
     }
     tile_store<O>((float*)nullptr, io.obs, row0, E.n, obs, false, mine);
@@ -249,11 +245,7 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_hist_kernel(const un
 // pass 2: bucket-major offsets (heaviest bucket first; chunks in order inside a bucket) and scatter.  The order inside one chunk's
 // slice of a bucket is arbitrary: the map only decides which thread runs which env, never a result.
 // key / perm point at the group's first env / thread slot, id0 is that env's index
-// split / rcount (may be NULL): the group's light / heavy boundary -- the number of envs in the buckets >= HEAVY_BUCKET0, i.e. whose key has
-// KEY_FULL or a robot contact -- and the group's refused-list counter, zeroed here for the launches that follow
-constexpr int HEAVY_BUCKET0 = ((0 * 6 + 2) * 14 + 0) * 2;
-static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned short* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks, int id0,
-                                                                           int* __restrict__ split, int* __restrict__ rcount) {
+static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const unsigned short* __restrict__ key, const int* __restrict__ hist, int* __restrict__ perm, int n, int nchunks, int id0) {
     __shared__ int s_pos[PERM_BUCKETS], s_warp[PERM_THREADS / 32];
     // thread t owns bucket PERM_BUCKETS-1-t (descending order): total over all chunks, prefix over the chunks before this one
     const int b = PERM_BUCKETS - 1 - (int)threadIdx.x;
@@ -267,7 +259,6 @@ static __global__ void __launch_bounds__(PERM_THREADS) perm_scatter_kernel(const
     int carry = 0;
     for (int w = 0; w < (int)(threadIdx.x >> 5); w++) carry += s_warp[w];
     if (b >= 0) s_pos[b] = carry + x - tot + pre;
-    if (blockIdx.x == 0 && b == HEAVY_BUCKET0 - 1) { if (split) *split = carry + x - tot; if (rcount) *rcount = 0; }
     __syncthreads();
     const int base = blockIdx.x * PERM_CHUNK;
     for (int i = base + threadIdx.x; i < min(n, base + PERM_CHUNK); i += PERM_THREADS) perm[atomicAdd(&s_pos[perm_bucket(key[i])], 1)] = id0 + i;
@@ -282,60 +273,43 @@ template <int W, typename E> __device__ __forceinline__ void row_store(E* g, int
     for (int k = 0; k < W; k++) g[(size_t)i * W + k] = reg[k];
 }
 
-// Dynamic shared memory per block: per thread, solver_slots() words of solver state (Jx + contact records, word-interleaved) -- or
-// heavy_slots() words in a launch that may run the heavy path (dense contact rows, panda_contact.cuh "split sub-step") -- aliased with
+// Dynamic shared memory per block: solver_slots() words per thread of solver state (Jx + contact records, word-interleaved), aliased with
 // the I/O row tile that is only live before and after the simulation phase.
-// One warp per block: a block is the unit the SM schedules and frees, so a warp of slow envs holds nothing but its own slot; 16 envs
-// per block in fp64 parity mode, where the heavy slab of 32 envs would not fit.
+// Threads per block: 128, except where the solver slab of 128 envs would exceed the 227 kB a block may own (fp64 parity mode on the
+// two-object scene: 416 slots x 8 B x 128 = 426 kB) -- those run 32-env blocks.
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-template <typename T, int TASK> constexpr int step_block() { return (size_t)heavy_slots(task_nobj(TASK)) * 32 * sizeof(T) <= SMEM_LIMIT ? 32 : 16; }
-template <typename T, int TASK, int CTRL> constexpr size_t step_smem_bytes(bool heavy) {
+template <typename T, int TASK> constexpr int step_block() { return (size_t)solver_slots(task_nobj(TASK)) * PG_STEP_BLOCK * sizeof(T) <= SMEM_LIMIT ? PG_STEP_BLOCK : 32; }
+template <typename T, int TASK, int CTRL> constexpr size_t step_smem_bytes() {
     constexpr int O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL), BS = step_block<T, TASK>();
     constexpr int W = O > NA ? (O > G ? O : G) : (NA > G ? NA : G);
-    const size_t solver = (size_t)(heavy ? heavy_slots(task_nobj(TASK)) : solver_slots(task_nobj(TASK))) * BS * sizeof(T), tile = (size_t)W * BS * sizeof(float);
+    constexpr size_t solver = (size_t)solver_slots(task_nobj(TASK)) * BS * sizeof(T), tile = (size_t)W * BS * sizeof(float);
     return solver > tile ? solver : tile;
 }
-template <typename T, int NOBJ> struct StepHooks {      // env_step_sim's window on the env's state in HBM
-    const EnvDev<T>& E; int i; T* q; T* qd; Obj<T>* ob;
-    __device__ __forceinline__ void commit(int) { store_state<T, NOBJ>(E, i, q, qd, ob); }
-    __device__ __forceinline__ void reload() { load_state<T, NOBJ>(E, i, q, qd, ob); }
-};
 template <typename T, int TASK, int CTRL>
 __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __grid_constant__ EnvDev<T> E, const StepIO io) {
     constexpr int NOBJ = task_nobj(TASK), O = task_obs_dim(TASK), G = task_goal_dim(TASK), NA = task_act_dim(TASK, CTRL), BS = step_block<T, TASK>();
-    static_assert(step_smem_bytes<T, TASK, CTRL>(true) <= SMEM_LIMIT, "solver slab exceeds the per-block shared memory of sm_100");
+    static_assert(step_smem_bytes<T, TASK, CTRL>() <= SMEM_LIMIT, "solver slab exceeds the per-block shared memory of sm_100");
     extern __shared__ __align__(16) unsigned char s_raw[];
     float* s_io = reinterpret_cast<float*>(s_raw);
     __shared__ double s_stats[6];
     const long long row0 = (long long)blockIdx.x * BS;
     const bool mapped = E.perm != nullptr;               // launch-uniform
-    // thread slot -> env
-    int t = (int)row0 + threadIdx.x, limit, base = 0;
-    const int* map = mapped ? E.perm + E.t0 : nullptr;
-    if (io.mode == MODE_LIGHT) { base = E.split[io.group]; limit = E.tcount - base; }
-    else if (io.mode == MODE_HEAVY) limit = E.split[io.group];
-    else if (io.mode == MODE_REFUSED) { limit = E.rcount[io.group]; map = E.rlist + E.t0; }
-    else limit = mapped ? E.tcount : E.n;
-    if (row0 >= limit) return;                           // block-uniform: launches over a split are sized for the worst case
-    const bool valid = t < limit;
-    const int i = (valid && map) ? map[base + t] : t;
+    const int t = (int)row0 + threadIdx.x;
+    const bool valid = t < (mapped ? E.tcount : E.n);
+    const int i = (valid && mapped) ? E.perm[E.t0 + t] : t;
     if (threadIdx.x < 6) s_stats[threadIdx.x] = 0.0;
     __syncthreads();                                     // s_stats is zeroed before any warp can atomicAdd into it
-    const bool first = io.s0 == 0, last = io.s1 == E.P.nsub;      // launch-uniform: the launch starts / may end the step of its envs
+    const bool first = io.s0 == 0, last = io.s1 == E.P.nsub;      // launch-uniform
     float act[NA];
-    if (first) { if (map) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA, float, BS>(s_io, io.actions, row0, E.n, act); }
+    if (first) { if (mapped) { if (valid) row_load<NA>(io.actions, i, act); } else tile_load<NA, float, BS>(s_io, io.actions, row0, E.n, act); }
     float obs[O], ag[G], dg[G], reward = 0.0f;
     unsigned char term = 0, trunc = 0;
-    bool finished = false;
     if (valid) {
         T q[ND], qd[ND], target[ND], qc[ND]; Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
         Contacts<T> C;
         C.st.base = reinterpret_cast<T*>(s_raw) + threadIdx.x; C.st.stride = BS; C.dropped = 0;
         load_state<T, NOBJ>(E, i, q, qd, ob);
-        const int sub0 = E.sub[i];
-        int s = sub0 < 0 ? 0 : (sub0 & SUB_MASK);
-        const bool have_target = sub0 >= 0 && (s > 0 || (sub0 & SUB_TARGET) != 0);
-        if (have_target) {
+        if (!first) {
 #pragma unroll
             for (int d = 0; d < ND; d++) target[d] = E.target[d * E.n + i];
         }
@@ -343,18 +317,15 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
         float tquat[4];
         if (first && io.target_quat) row_load<4>(io.target_quat, i, tquat);
         const long long clk0 = E.dbg ? clock64() : 0;
-        StepHooks<T, NOBJ> hooks{E, i, q, qd, ob};
-        int status = SUB_OK;
-        if (s < io.s1) status = env_step_sim<T, TASK, CTRL>(E.M, E.S, q, qd, ob, act, (first && io.target_quat) ? tquat : nullptr, C, sched_key, target, qc, s, io.s1, E.P.nsub,
-                                                            have_target, io.heavy_ok != 0, hooks);
-        if (E.dbg) { E.dbg[2 * (size_t)(E.t0 + base + t)] = clock64() - clk0; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); E.dbg[2 * (size_t)(E.t0 + base + t) + 1] = (long long)sched_key | ((long long)smid << 16) | ((long long)io.mode << 32); }
+        env_step_sim<T, TASK, CTRL, BS>(E.M, E.S, q, qd, ob, act, (first && io.target_quat) ? tquat : nullptr, C, sched_key, target, qc, io.s0, io.s1, E.P.nsub);
+        if (E.dbg) { E.dbg[2 * (size_t)(E.t0 + t)] = clock64() - clk0; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); E.dbg[2 * (size_t)(E.t0 + t) + 1] = (long long)sched_key | ((long long)smid << 16); }
         if (C.dropped > 0) atomicAdd(&s_stats[5], (double)C.dropped);
-        if (status == SUB_REFUSED) { const int k = atomicAdd(&E.rcount[io.group], 1); E.rlist[E.t0 + k] = i; }
-        finished = s == E.P.nsub;
         double goal[6];
-        if (finished) {     // the goal is only needed now: loaded after the simulation so that it does not occupy registers across the solver
+        if (last) {     // the goal is only needed now: loaded after the simulation so that it does not occupy registers across the solver
             load_goal(E, i, goal);
             env_step_finish<T, TASK>(E.M, E.reward_type, q, qd, qc, ob, goal, E.P.thr64, obs, ag, dg, reward, term);
+        }
+        if (last) {
             int steps = E.steps[i] + 1;
             trunc = steps >= task_max_steps(TASK);
             float ret = E.ret[i] + reward;
@@ -374,11 +345,10 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
                 E.episode[i] = ep; steps = 0; ret = 0.0f; sched_key = 0;
                 env_observe<T, TASK>(E.M, q, qd, q, ob, goal, obs, ag, dg);
             }
-            E.steps[i] = steps; E.ret[i] = ret; E.sub[i] = -1;
+            E.steps[i] = steps; E.ret[i] = ret;
         } else {
 #pragma unroll
             for (int d = 0; d < ND; d++) E.target[d * E.n + i] = target[d];
-            E.sub[i] = s | SUB_TARGET;
         }
         store_state<T, NOBJ>(E, i, q, qd, ob);
         E.ccount[i] = (unsigned short)sched_key;
@@ -389,14 +359,14 @@ __global__ void __launch_bounds__((step_block<T, TASK>())) step_kernel(const __g
         return;
     }
     __syncthreads();    // the solver slab is dead for every thread of the block: reuse it as the output tile
-    if (map) {
-        if (finished) { row_store<O>(io.obs, i, obs); row_store<G>(io.ag, i, ag); row_store<G>(io.dg, i, dg); }
-    } else {            // identity map: the launch owns the heavy path, every valid env finishes
+    if (mapped) {
+        if (valid) { row_store<O>(io.obs, i, obs); row_store<G>(io.ag, i, ag); row_store<G>(io.dg, i, dg); }
+    } else {
         tile_store<O, float, BS>(s_io, io.obs, row0, E.n, obs, true, valid);
         tile_store<G, float, BS>(s_io, io.ag, row0, E.n, ag, true, valid);
         tile_store<G, float, BS>(s_io, io.dg, row0, E.n, dg, true, valid);
     }
-    if (finished) {
+    if (valid) {
         if (io.reward) io.reward[i] = reward;
         if (io.terminated) io.terminated[i] = term;
         if (io.truncated) io.truncated[i] = trunc;
@@ -427,7 +397,7 @@ __global__ void __launch_bounds__(BLOCK) set_state_kernel(const __grid_constant_
     for (int d = 0; d < ND; d++) { E.q[d * n + i] = (T)r[d]; E.qd[d * n + i] = (T)r[9 + d]; }
     for (int k = 0; k < 13 * nobj; k++) E.obj[(size_t)k * n + i] = (T)r[18 + k];
     for (int k = 0; k < G; k++) E.goal[k * n + i] = r[18 + 13 * nobj + k];
-    E.steps[i] = (int)r[SD - 1]; E.sub[i] = -1;
+    E.steps[i] = (int)r[SD - 1];
 }
 // calculateInverseKinematics (pybullet.py:479-497) on `link` from the current joint state: target [n,3] + quaternion [n,4] (normalised
 // here; the reference's KAT test/pybullet_test.py:265 passes an un-normalised one) -> 9 joint values.  link 11 with out7 != 0 is the

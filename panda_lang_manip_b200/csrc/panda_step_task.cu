@@ -12,18 +12,17 @@ extern long long g_launches;
 
 template <typename T, int TASK> void launch_step(const EnvDev<T>& E, int ctrl, const StepIO& io, cudaStream_t st) {
     constexpr int BS = step_block<T, TASK>();
-    // launches over one side of a split (or the refused list) are sized for the worst case: the count lives on the device, surplus blocks exit at once
     const int grid = ((E.perm ? E.tcount : E.n) + BS - 1) / BS;
-    if (ctrl == CTRL_EE) step_kernel<T, TASK, CTRL_EE><<<grid, BS, step_smem_bytes<T, TASK, CTRL_EE>(io.heavy_ok != 0), st>>>(E, io);
-    else step_kernel<T, TASK, CTRL_JOINTS><<<grid, BS, step_smem_bytes<T, TASK, CTRL_JOINTS>(io.heavy_ok != 0), st>>>(E, io);
+    if (ctrl == CTRL_EE) step_kernel<T, TASK, CTRL_EE><<<grid, BS, step_smem_bytes<T, TASK, CTRL_EE>(), st>>>(E, io);
+    else step_kernel<T, TASK, CTRL_JOINTS><<<grid, BS, step_smem_bytes<T, TASK, CTRL_JOINTS>(), st>>>(E, io);
     g_launches++;
 }
 // > 48 KB of dynamic shared memory needs an opt-in per function AND per device (function attributes live in the device's context):
 // pg_create calls this for the handle's device; errors are reported to the caller.
 template <typename T, int TASK> cudaError_t configure_step(void) {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_EE>(true))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_JOINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_JOINTS>(true))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_EE>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_JOINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes<T, TASK, CTRL_JOINTS>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_EE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(step_kernel<T, TASK, CTRL_JOINTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }

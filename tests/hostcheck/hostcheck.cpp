@@ -44,7 +44,7 @@ template <typename T, int TASK, int CTRL> static void env_step_t(int reward, con
     for (int i = 0; i < ND; i++) { q[i] = (T)st[i]; qd[i] = (T)st[9 + i]; }
     for (int o = 0; o < NOBJ; o++) { const double* p = st + 18 + 13 * o; ob[o].pos = mk<T>((T)p[0], (T)p[1], (T)p[2]); ob[o].qx = (T)p[3]; ob[o].qy = (T)p[4]; ob[o].qz = (T)p[5]; ob[o].qw = (T)p[6]; ob[o].lin = mk<T>((T)p[7], (T)p[8], (T)p[9]); ob[o].ang = mk<T>((T)p[10], (T)p[11], (T)p[12]); }
     for (int k = 0; k < 6; k++) goal[k] = st[44 + k];
-    static Contacts<T> C; static T slab[heavy_slots(1) > solver_slots(2) ? heavy_slots(1) : solver_slots(2)]; C.st.base = slab; C.st.stride = 1; C.dropped = 0;
+    static Contacts<T> C; static T slab[solver_slots(2)]; C.st.base = slab; C.st.stride = 1;
     int mc = 0; T target[ND]; env_step<T, TASK, CTRL>(M, S, reward, q, qd, ob, goal, action, nullptr, obs, ag, dg, *rew, *succ, C, mc, target);
     for (int i = 0; i < ND; i++) { st[i] = q[i]; st[9 + i] = qd[i]; }
     for (int o = 0; o < NOBJ; o++) { double* p = st + 18 + 13 * o; p[0] = ob[o].pos.x; p[1] = ob[o].pos.y; p[2] = ob[o].pos.z; p[3] = ob[o].qx; p[4] = ob[o].qy; p[5] = ob[o].qz; p[6] = ob[o].qw; p[7] = ob[o].lin.x; p[8] = ob[o].lin.y; p[9] = ob[o].lin.z; p[10] = ob[o].ang.x; p[11] = ob[o].ang.y; p[12] = ob[o].ang.z; }
