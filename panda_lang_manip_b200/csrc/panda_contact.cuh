@@ -129,6 +129,20 @@ constexpr int JX_SLOTS = 42;            // Jx: per arm joint j, angular (z_j) an
 PG_HD constexpr int max_contacts(int nobj) { return nobj <= 1 ? 10 : 22; }
 PG_HD constexpr int solver_slots(int nobj) { return JX_SLOTS + max_contacts(nobj) * REC; }
 enum { C_P = 0, C_N = 3, C_INVD = 6, C_RHS = 9, C_APP = 12, C_MU = 15, C_CODE = 16 };
+// Response cache of robot-only scenes (Reach): while an env has at most YC_MAX contacts -- two fingertips on the table are four -- the
+// records of the contacts YC_MAX .. 9 are unused, and the three rows' operational-space impulse responses y = Lambda w (8 words each) of
+// the first YC_MAX contacts live there: a row application is then 8 shared-memory loads + 8 FMAs instead of the 40-FMA Lambda product.
+constexpr int YC_MAX = 4;
+// Measured build variants (profiles/r2_solver_structure_ab): PG_YC = the response cache, PG_OOL = the full sweep as a non-inlined function,
+// PG_WATCH_EE (panda_env.cuh) = the watched sweep for ee control.  None of them beats round 1's structure on B200, so all default to 0.
+#ifndef PG_YC
+#define PG_YC 0
+#endif
+#ifndef PG_OOL
+#define PG_OOL 0
+#endif
+PG_HD constexpr bool yc_supported(int nobj) { return PG_YC && nobj == 0 && (max_contacts(nobj) - YC_MAX) * REC >= YC_MAX * 24; }
+PG_HD constexpr int yc_slot(int c, int k) { return JX_SLOTS + YC_MAX * REC + (c * 3 + k) * 8; }
 
 template <typename T> struct CStore {   // per-thread view of the shared-memory slab (host test build: a plain array, stride 1)
     T* base; int stride;
@@ -141,6 +155,7 @@ template <typename T> struct Contacts {
     int nB, nA;                 // contacts are collected in type order: [0, nB) object vertex on a plane, [nB, nB + nA) robot box on the table, then generic
     bool near;                  // the gripper is within 3 cm of the table or inside an object's broad-phase sphere (scheduling hint)
     bool capped;                // the last solve ran (nearly) all 50 sweeps (scheduling hint)
+    bool ycache;                // the rows' impulse responses are cached in the store (robot-only scenes with at most YC_MAX contacts, see YC_SLOT)
     PG_HD T& f(int c, int k) { return st.at(JX_SLOTS + c * REC + k); }
     PG_HD T& jx(int j, int a) { return st.at(6 * j + a); }
 };
@@ -206,6 +221,7 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
         }
     }
     C.nA = C.n - C.nB;
+    C.ycache = yc_supported(NOBJ) && C.n <= YC_MAX;
     // 3. robot box <-> object, both directions
     if (NOBJ > 0) {
 #pragma unroll
@@ -362,6 +378,11 @@ template <int AX, int SG, typename T, int NOBJ> struct AxisRow {
         F8[I1] += m1 * di; F8[I2] += m2 * di; F8[3 + AX] += T(SG) * di; F8[6] += f6 * di; F8[7] += f7 * di;
     }
     PG_HD T den(const OpSpace<T>& Op) const { T y[8]; lam(Op, y); return jdv(y); }
+    PG_HD void apply_cached(const T* y, T di, T* d8, T* F8) const {      // y = lam(Op) from the response cache
+#pragma unroll
+        for (int k = 0; k < 8; k++) d8[k] += y[k] * di;
+        F8[I1] += m1 * di; F8[I2] += m2 * di; F8[3 + AX] += T(SG) * di; F8[6] += f6 * di; F8[7] += f7 * di;
+    }
 };
 // Object-vs-plane row along SG * e_AX (the object is body A): J = [e; r x e], W = [e/m; Iinv (r x e)] with r x e_AX two-sparse.
 template <int AX, int SG, typename T> struct ObjAxisRow {
@@ -402,9 +423,14 @@ PG_HD void rows_setup(const Scene<T>& S, const World<T, NOBJ>& W, const OpSpace<
             T den = T(0), rel = T(0);
             if (ROBOT) {
                 if (NOBJ == 0 || (X.table && X.rb >= 0)) {
-                    if (k == 0) { AxisRow<2, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
-                    else if (k == 1) { AxisRow<1, -1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
-                    else { AxisRow<0, 1, T, NOBJ> r(Op, X); den += r.den(Op); rel += r.jdv(Op.v); }
+                    T y[8];
+                    if (k == 0) { AxisRow<2, 1, T, NOBJ> r(Op, X); r.lam(Op, y); den += r.jdv(y); rel += r.jdv(Op.v); }
+                    else if (k == 1) { AxisRow<1, -1, T, NOBJ> r(Op, X); r.lam(Op, y); den += r.jdv(y); rel += r.jdv(Op.v); }
+                    else { AxisRow<0, 1, T, NOBJ> r(Op, X); r.lam(Op, y); den += r.jdv(y); rel += r.jdv(Op.v); }
+                    if (yc_supported(NOBJ) && C.ycache) {
+#pragma unroll
+                        for (int a = 0; a < 8; a++) C.st.at(yc_slot(c, k) + a) = y[a];
+                    }
                 } else if (X.rb >= 0) { T w[8], y[8]; robot_wrench<T, NOBJ>(Op, X, d, w); lambda_mul(Op, w, y); den += dot8(w, y); rel += dot8(w, Op.v); }
             }
 #pragma unroll
@@ -510,7 +536,12 @@ PG_HD bool pgs_solve(const T* max_imp, const Scene<T>& S, const World<T, NOBJ>& 
                     di = C.f(c, C_RHS) - app * (X.soft ? S.soft_cfm * inv : T(0)) - row.jdv(d8) * inv;
                     di = fmax(di, -app);              // accumulated normal impulse >= 0, on the change (short dependency chain)
                     C.f(c, C_APP) = app + di;
-                    row.apply(Op, di, d8, F8);
+                    if (yc_supported(NOBJ) && C.ycache) {
+                        T y[8];
+#pragma unroll
+                        for (int a = 0; a < 8; a++) y[a] = C.st.at(yc_slot(c, 0) + a);
+                        row.apply_cached(y, di, d8, F8);
+                    } else row.apply(Op, di, d8, F8);
                 } else if constexpr (K == KIND_OBJ_PLANE) {       // object vertex on the table / ground plane
                     const int o = (NOBJ == 2 && X.sgo[NOBJ - 1] != T(0)) ? 1 : 0;
                     ObjAxisRow<2, 1, T> row(X.P - ob[o].pos);
@@ -559,11 +590,16 @@ PG_HD bool pgs_solve(const T* max_imp, const Scene<T>& S, const World<T, NOBJ>& 
                         V3<T> m = cross(r, fdir);
                         T fd = dot(Op.hy, fdir);
                         T w[8] = {m.x, m.y, m.z, fdir.x, fdir.y, T(0), X.rb == 1 ? fd : T(0), X.rb == 2 ? -fd : T(0)};
+                        if (yc_supported(NOBJ) && C.ycache) {      // the two tangent rows' cached responses
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            d8[k] += Op.L[sidx(k, 0)] * w[0] + Op.L[sidx(k, 1)] * w[1] + Op.L[sidx(k, 2)] * w[2] + Op.L[sidx(k, 3)] * w[3] + Op.L[sidx(k, 4)] * w[4]
-                                   + Op.L[sidx(k, 6)] * w[6] + Op.L[sidx(k, 7)] * w[7];
-                            F8[k] += w[k];
+                            for (int k = 0; k < 8; k++) { d8[k] += C.st.at(yc_slot(c, 1) + k) * d1 + C.st.at(yc_slot(c, 2) + k) * d2; F8[k] += w[k]; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                d8[k] += Op.L[sidx(k, 0)] * w[0] + Op.L[sidx(k, 1)] * w[1] + Op.L[sidx(k, 2)] * w[2] + Op.L[sidx(k, 3)] * w[3] + Op.L[sidx(k, 4)] * w[4]
+                                       + Op.L[sidx(k, 6)] * w[6] + Op.L[sidx(k, 7)] * w[7];
+                                F8[k] += w[k];
+                            }
                         }
                     }
                 } else if constexpr (ROBOT) {
@@ -649,7 +685,70 @@ PG_HD void world_inertia(const Scene<T>& S, int o, World<T, NOBJ>& W) {
     W.Iinv[o][5] = ix * R.X.z * R.X.z + iy * R.Y.z * R.Y.z + iz * R.Z.z * R.Z.z;
 }
 
-template <typename T, int NOBJ, bool WATCH_LIMITS, bool GENERIC_MOTORS = false>
+// The full sweep (every arm-limit row real) of the env path lives in a separate, NON-INLINED function with its own register allocation:
+// it runs only for envs whose arm limits engage (never in random-action rollouts, sometimes under scripted policies), and inlined next
+// to the watched sweep it cost every env 13-25 % (code size and register allocation of the hot loop: round 1 therefore gave ee control the
+// full sweep for everybody).  What it needs is handed over in a local-memory record; the contact records already sit in shared memory.
+#ifdef __CUDACC__
+#define PG_NOINLINE __noinline__
+#else
+#define PG_NOINLINE __attribute__((noinline))
+#endif
+template <typename T, int NOBJ> struct FullSolveIO {
+    T Minv[ND][ND];
+    JointRows<T> R;
+    T max_imp[ND];
+    OpSpace<T> Op;
+    Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+    T Iinv[NOBJ > 0 ? NOBJ : 1][6];
+    T dvq[ND]; V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];     // out
+    int n, nr, nB, nA, ycache;                  // in: the collection's counters
+    int capped, any_limit;                      // out
+};
+template <typename T, int NOBJ, int STRIDE>
+PG_NOINLINE
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+void full_solve(const Scene<T>& S, FullSolveIO<T, NOBJ>& H, T* sbase) {
+    Contacts<T> C; C.st.base = sbase; C.st.stride = STRIDE;
+    C.n = H.n; C.nr = H.nr; C.nB = H.nB; C.nA = H.nA; C.cap = max_contacts(NOBJ); C.dropped = 0; C.near = false; C.capped = false; C.ycache = H.ycache != 0;
+    T Minv[ND][ND], mx[ND];
+#pragma unroll
+    for (int i = 0; i < ND; i++) {
+#pragma unroll
+        for (int j = 0; j < ND; j++) Minv[i][j] = H.Minv[i][j];
+        mx[i] = H.max_imp[i];
+    }
+    World<T, NOBJ> W;
+    Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) {
+        ob[o] = H.ob[o];
+#pragma unroll
+        for (int k = 0; k < 6; k++) W.Iinv[o][k] = H.Iinv[o][k];
+    }
+    JointRows<T> R = H.R;
+    T dvq[ND];
+    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
+#pragma unroll
+    for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+    for (int c = 0; c < C.n; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
+    pgs_solve<T, NOBJ, false, true>(mx, S, W, H.Op, Minv, R, C, ob, H.nr > 0, dvq, dvl, dva);
+    bool any = false;       // did an arm limit row actually carry impulse?
+#pragma unroll
+    for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
+#pragma unroll
+    for (int d = 0; d < ND; d++) H.dvq[d] = dvq[d];
+#pragma unroll
+    for (int o = 0; o < NOBJ; o++) { H.dvl[o] = dvl[o]; H.dva[o] = dva[o]; }
+    H.capped = C.capped; H.any_limit = any;
+}
+
+// WATCH_LIMITS (the env path): watched arm-limit rows inline, the full sweep out of line; !WATCH_LIMITS (bare worlds): the full sweep inline.
+template <typename T, int NOBJ, bool WATCH_LIMITS, bool GENERIC_MOTORS = false, int STRIDE = 1>
 PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& full_sweep, bool& limits_active,
                        const T* mot = nullptr) {
     T sn[7], cs[7], Minv[ND][ND], qdd[ND];
@@ -682,7 +781,6 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
     // the solve restarts from zero impulses with every row real (a watched row is an exact no-op: the result is the full sweep's, up to
     // FMA-contraction differences between the two loop instantiations).  Which of the two ran is a function of the env's own state,
     // never of the batch or the schedule.
-    const int nc = C.n;
     bool fast = WATCH_LIMITS && !full_sweep && !arm_limit_violated(M, q);
 #ifdef PG_HOST_DEBUG
     if (!fast) g_dbg_full_starts++;
@@ -691,207 +789,52 @@ PG_HD void env_substep(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const 
     if (fast) live = pgs_solve<T, NOBJ, true>(M.max_imp, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
     if (!fast || live) {
         full_sweep = true;
-        if (live) {
 #ifdef PG_HOST_DEBUG
-            g_dbg_fallbacks++;
+        if (live) g_dbg_fallbacks++;
 #endif
-#pragma unroll
-            for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
-#pragma unroll
-            for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
-            for (int c = 0; c < nc; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
-        }
-        pgs_solve<T, NOBJ, false>(M.max_imp, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
-        bool any = false;       // did an arm limit row actually carry impulse?  (decides whether the next step starts with the full sweep)
-#pragma unroll
-        for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
-        limits_active = limits_active || any || live;
-    }
-#pragma unroll
-    for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) { ob[o].lin = ob[o].lin + dvl[o]; ob[o].ang = ob[o].ang + dva[o]; obj_integrate(ob[o]); }
-}
-
-
-// ---------------------------------------------------------------------------------------------- task sub-step: light path inline, robot path out of line
-// Scenes with at most one object run every sub-step through one of two paths, chosen by the env's own state (never by the batch or the
-// schedule, so results do not depend on how a batch is launched):
-//
-//   light  no robot collision box is in contact and the arm joint limits are slack: the watched-limit sweep plus object-on-plane rows
-//          (pgs_solve<FAST, ROBOT = false>) -- the only solver loop that is inlined into the step kernel, ~1/3 of the code of the full one;
-//   robot  a robot box touches the table or the object, or an arm limit is engaged (or a watched row trips): the full operational-space
-//          solver (robot-on-table rows, generic rows, both sweep variants) in a separate, NON-INLINED function with its own register
-//          allocation.  What it needs from the sub-step's set-up is handed over in a local-memory record (~1 kB: the call happens
-//          once per sub-step, the copies are noise next to 50 sweeps), the contact records and Jx already sit in shared memory.
-//
-// Round 1 inlined both sweep variants and all contact kinds into one kernel body: with ee control the second instantiation cost 13-25 %
-// (code size, register allocation of the hot loop), which is why ee control ran the full sweep for everybody.  Out of line, every
-// configuration gets the watched sweep on its light path.
-// (A dense variant of the robot path -- every contact row as a dense Jacobian row + impulse response in [joint velocities, object
-// twist], 101 words per contact -- was built and measured in round 2: same results, 3x shorter worst-case sub-step for PickAndPlace, but
-// its 151 kB per 32 envs leave one such warp per SM and the step got slower; profiles/r2_split_experiment)
-#ifdef __CUDACC__
-#define PG_NOINLINE __noinline__
-#else
-#define PG_NOINLINE __attribute__((noinline))
-#endif
-PG_HD constexpr bool split_supported(int nobj) { return nobj <= 1; }
-
-template <typename T, int NOBJ> struct RobotIO {
-    T Minv[ND][ND];
-    JointRows<T> R;
-    T qd[ND], max_imp[ND];
-    V3<T> O6, hy;
-    Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
-    T Iinv[NOBJ > 0 ? NOBJ : 1][6];
-    T z[ND + 6 * (NOBJ > 0 ? NOBJ : 1)];        // out: velocity change [dvq, dvl, dva]
-    int n, nr, nB, nA, fast;                    // in: contact counters of the collection, start with the watched-limit sweep
-    int capped, any_limit;                      // out: ran all 50 sweeps; an arm limit row carries impulse after a full solve
-};
-
-template <typename T, int NOBJ, int STRIDE>
-PG_NOINLINE
-#ifdef __CUDACC__
-__host__ __device__
-#endif
-void robot_solve(const Scene<T>& S, RobotIO<T, NOBJ>& H, T* sbase) {
-    Contacts<T> C; C.st.base = sbase; C.st.stride = STRIDE;
-    C.n = H.n; C.nr = H.nr; C.nB = H.nB; C.nA = H.nA; C.cap = max_contacts(NOBJ); C.dropped = 0; C.near = false; C.capped = false;
-    T Minv[ND][ND], qd[ND], mx[ND];
-#pragma unroll
-    for (int i = 0; i < ND; i++) {
-#pragma unroll
-        for (int j = 0; j < ND; j++) Minv[i][j] = H.Minv[i][j];
-        qd[i] = H.qd[i]; mx[i] = H.max_imp[i];
-    }
-    OpSpace<T> Op; Op.O6 = H.O6; Op.hy = H.hy;
-    const bool robot_contacts = H.nr > 0;
-    if (robot_contacts) opspace_lambda<T>(Minv, qd, C, Op);
-    World<T, NOBJ> W;
-    Obj<T> ob[NOBJ > 0 ? NOBJ : 1];
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) {
-        ob[o] = H.ob[o];
-#pragma unroll
-        for (int k = 0; k < 6; k++) W.Iinv[o][k] = H.Iinv[o][k];
-    }
-    rows_setup<T, NOBJ, true>(S, W, Op, ob, C);
-    JointRows<T> R = H.R;
-    T dvq[ND];
-    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
-#pragma unroll
-    for (int d = 0; d < ND; d++) dvq[d] = T(0);
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
-    const bool fast = H.fast != 0;
-    bool live = false, any = false;
-    if (fast) live = pgs_solve<T, NOBJ, true, true>(mx, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
-    if (!fast || live) {
-        if (live) {
-#ifdef PG_HOST_DEBUG
-            g_dbg_fallbacks++;
-#endif
-#pragma unroll
-            for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
-#pragma unroll
-            for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
-            for (int c = 0; c < C.n; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
-        }
-        pgs_solve<T, NOBJ, false, true>(mx, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
-#pragma unroll
-        for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
-    }
-#pragma unroll
-    for (int d = 0; d < ND; d++) H.z[d] = dvq[d];
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) {
-        H.z[ND + 6 * o] = dvl[o].x; H.z[ND + 6 * o + 1] = dvl[o].y; H.z[ND + 6 * o + 2] = dvl[o].z;
-        H.z[ND + 6 * o + 3] = dva[o].x; H.z[ND + 6 * o + 4] = dva[o].y; H.z[ND + 6 * o + 5] = dva[o].z;
-    }
-    H.capped = C.capped; H.any_limit = any;
-}
-
-// One 2 ms stepSimulation of a task scene with at most one object.  `flag_full` is the env's "an arm limit row carried impulse in its
-// last full solve" bit (it travels in the scheduling key from sub-step to sub-step, a function of the env's own history).
-template <typename T, int NOBJ, int STRIDE>
-PG_HD void env_substep_task(const Model<T>& M, const Scene<T>& S, T* q, T* qd, const T* target, Obj<T>* ob, Contacts<T>& C, bool& flag_full) {
-    static_assert(split_supported(NOBJ), "two-object scenes run env_substep");
-    // contacts first (they depend on the poses only): the collection's registers are dead before the dynamics needs its own
-    T sn[7], cs[7];
-#pragma unroll
-    for (int i = 0; i < 7; i++) sincos_t(q[i], sn[i], cs[i]);
-    World<T, NOBJ> W;
-    world_robot(M, S, q, sn, cs, W);
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) W.Ro[o] = quat_rot(ob[o].qx, ob[o].qy, ob[o].qz, ob[o].qw);
-    collect_contacts<T, NOBJ>(S, W, ob, C);
-    T Minv[ND][ND], qdd[ND];
-    robot_dynamics_sc(M, q, qd, sn, cs, Minv, qdd);
-#pragma unroll
-    for (int d = 0; d < ND; d++) qd[d] += qdd[d] * Consts<T>::dt;
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) { obj_unconstrained(S, o, ob[o], W.Ro[o]); world_inertia(S, o, W); }
-    JointRows<T> R;
-    joint_rows_setup<true, false>(M, q, qd, target, Minv, R);
-    T dvq[ND];
-    V3<T> dvl[NOBJ > 0 ? NOBJ : 1], dva[NOBJ > 0 ? NOBJ : 1];
-#pragma unroll
-    for (int d = 0; d < ND; d++) dvq[d] = T(0);
-#pragma unroll
-    for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
-    bool need_full = flag_full || arm_limit_violated(M, q);
-    bool robot = C.nr > 0 || need_full;
-#ifdef PG_HOST_DEBUG
-    if (need_full) g_dbg_full_starts++;
-#endif
-    if (!robot) {
-        OpSpace<T> Op;
-        rows_setup<T, NOBJ, false>(S, W, Op, ob, C);
-        const bool live = pgs_solve<T, NOBJ, true, false>(M.max_imp, S, W, Op, Minv, R, C, ob, false, dvq, dvl, dva);
-        if (live) {     // a watched arm-limit row would have engaged: this sub-step belongs to the robot path, every row real, from zero impulses
-#ifdef PG_HOST_DEBUG
-            g_dbg_fallbacks++;
-#endif
-            robot = true; need_full = true;
-#pragma unroll
-            for (int d = 0; d < ND; d++) { R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
-            { const int dropped = C.dropped; collect_contacts<T, NOBJ>(S, W, ob, C); C.dropped = dropped; }   // the light row set-up consumed the parked distances: same poses, same records
-        } else flag_full = false;
-    }
-    if (robot) {
-        RobotIO<T, NOBJ> H;
-        {
-            OpSpace<T> Op;
-            opspace_jx<T, NOBJ>(W, C, Op);
-            H.O6 = Op.O6; H.hy = Op.hy;
+        if (WATCH_LIMITS && PG_OOL) {     // every row real, from zero impulses, out of line
+            FullSolveIO<T, NOBJ> H;
 #pragma unroll
             for (int i = 0; i < ND; i++) {
 #pragma unroll
                 for (int j = 0; j < ND; j++) H.Minv[i][j] = Minv[i][j];
-                H.qd[i] = qd[i]; H.max_imp[i] = M.max_imp[i];
+                H.max_imp[i] = M.max_imp[i];
             }
-            H.R = R;
+            H.R = R; H.Op = Op;
 #pragma unroll
             for (int o = 0; o < NOBJ; o++) {
                 H.ob[o] = ob[o];
 #pragma unroll
                 for (int k = 0; k < 6; k++) H.Iinv[o][k] = W.Iinv[o][k];
             }
-            H.n = C.n; H.nr = C.nr; H.nB = C.nB; H.nA = C.nA; H.fast = need_full ? 0 : 1;
+            H.n = C.n; H.nr = C.nr; H.nB = C.nB; H.nA = C.nA; H.ycache = C.ycache;
+            full_solve<T, NOBJ, STRIDE>(S, H, C.st.base);
+#pragma unroll
+            for (int d = 0; d < ND; d++) dvq[d] = H.dvq[d];
+#pragma unroll
+            for (int o = 0; o < NOBJ; o++) { dvl[o] = H.dvl[o]; dva[o] = H.dva[o]; }
+            C.capped = H.capped != 0;
+            limits_active = limits_active || H.any_limit != 0 || live;
+        } else {
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < ND; d++) { dvq[d] = T(0); R.mot_app[d] = T(0); R.lim_app[2 * d] = T(0); R.lim_app[2 * d + 1] = T(0); }
+#pragma unroll
+                for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(0, 0, 0); dva[o] = mk<T>(0, 0, 0); }
+                for (int c = 0; c < C.n; c++) { C.f(c, C_APP) = T(0); C.f(c, C_APP + 1) = T(0); C.f(c, C_APP + 2) = T(0); }
+            }
+            pgs_solve<T, NOBJ, false>(M.max_imp, S, W, Op, Minv, R, C, ob, robot_contacts, dvq, dvl, dva);
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < 14; r++) any = any || R.lim_app[r] > T(0);
+            limits_active = limits_active || any || live;
         }
-        robot_solve<T, NOBJ, STRIDE>(S, H, C.st.base);
-#pragma unroll
-        for (int d = 0; d < ND; d++) dvq[d] = H.z[d];
-#pragma unroll
-        for (int o = 0; o < NOBJ; o++) { dvl[o] = mk<T>(H.z[ND + 6 * o], H.z[ND + 6 * o + 1], H.z[ND + 6 * o + 2]); dva[o] = mk<T>(H.z[ND + 6 * o + 3], H.z[ND + 6 * o + 4], H.z[ND + 6 * o + 5]); }
-        C.capped = H.capped != 0;
-        flag_full = H.any_limit != 0;
     }
 #pragma unroll
     for (int d = 0; d < ND; d++) { qd[d] += dvq[d]; q[d] += qd[d] * Consts<T>::dt; }
 #pragma unroll
     for (int o = 0; o < NOBJ; o++) { ob[o].lin = ob[o].lin + dvl[o]; ob[o].ang = ob[o].ang + dva[o]; obj_integrate(ob[o]); }
 }
+
 
 }  // namespace pg

@@ -200,34 +200,23 @@ PG_HD void env_step_sim(const Model<T>& M, const Scene<T>& S, T* q, T* qd, Obj<T
                         T* target, T* qc, int s0 = 0, int s1 = 20, int nsub = 20) {
     constexpr int NOBJ = task_nobj(TASK);
     if (s0 == 0) env_set_action<T, TASK, CTRL>(M, q, qd, action, target_quat, target);
+    // sticky: once an arm limit engaged, later sub-steps (and, through the key's KEY_FULL bit, the next segment / step) start with the
+    // full sweep; it is dropped again after a segment in which no arm limit row carried impulse
+    bool full_sweep = (sched_key & KEY_FULL) != 0, limits_active = false;
     int nsub_contact = 0; bool near = false;
-    if constexpr (split_supported(NOBJ)) {
-        // light path inline / robot path out of line (env_substep_task); the env's "an arm limit carried impulse" bit travels in the key from
-        // sub-step to sub-step: a function of the env's own history, whatever the segmentation of the step
-        bool flag_full = (sched_key & KEY_FULL) != 0;
+    {
         for (int s = s0; s < s1; s++) {
             if (s == nsub - 1) {
 #pragma unroll
                 for (int d = 0; d < ND; d++) qc[d] = q[d];   // the link-transform cache is refreshed at the start of each sub-step
             }
-            env_substep_task<T, NOBJ, STRIDE>(M, S, q, qd, target, ob, C, flag_full);
-            if (C.n > 0) nsub_contact++;
-            near = near || C.near;
-        }
-        sched_key = (C.n < 31 ? C.n : 31) | (C.nr > 0 ? KEY_ROBOT : 0) | ((near || nsub_contact > 0) ? KEY_NEAR : 0) | (C.capped ? KEY_CAPPED : 0) | (flag_full ? KEY_FULL : 0);
-    } else {
-        // two-object scenes: everything inline, sticky full sweep -- once an arm limit engaged, later sub-steps of the launch (and, through the
-        // key's KEY_FULL bit, the next launch) start with the full sweep; dropped after a launch in which no arm limit row carried impulse
-        bool full_sweep = (sched_key & KEY_FULL) != 0, limits_active = false;
-        for (int s = s0; s < s1; s++) {
-            if (s == nsub - 1) {
-#pragma unroll
-                for (int d = 0; d < ND; d++) qc[d] = q[d];
-            }
-            // watched arm-limit rows: a measured policy -- +25 % with joint control, -13 % with ee control (contact rows dominate there and the
-            // second solver instantiation schedules worse), so it is enabled for joint control only.  A rolled (local-memory) full-sweep
-            // fallback inside one solver loop was tried in round 2: 3-10x slower (local loads / stores inside the sweep loop), removed.
-            env_substep<T, NOBJ, CTRL == CTRL_JOINTS>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
+            // watched arm-limit rows: a measured policy -- +25 % with joint control, -37..55 % with ee control (contact rows dominate there), so
+            // it is enabled for joint control only.  Round 2 re-measured the alternatives (full sweep out of line, watched sweep for ee
+            // control, a rolled local-memory fallback inside the one loop: 3-10x slower): profiles/r2_solver_structure_ab.
+#ifndef PG_WATCH_EE
+#define PG_WATCH_EE 0
+#endif
+            env_substep<T, NOBJ, (PG_WATCH_EE || CTRL == CTRL_JOINTS), false, STRIDE>(M, S, q, qd, target, ob, C, full_sweep, limits_active);
             if (C.n > 0) nsub_contact++;
             near = near || C.near;
         }
