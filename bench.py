@@ -307,6 +307,24 @@ def run_gpu(args):
                 "transitions_per_s": M / (ms / 1e3), "ms": ms, "achieved_gbs": nbytes / (ms / 1e3) / 1e9, "bytes_per_transition": 16 + 3 * G * 4 + 4,
                 "achieved_gbs_in_sector_terms": sector_bytes / (ms / 1e3) / 1e9, "sector_bytes_per_transition": 16 + 2 * 32 * sectors + G * 4 + 4,
                 "note": "random row gather: DRAM moves 32-byte sectors, so the sector figure is the one to hold against the HBM peak"}
+            if label == "dense_24B_rows":
+                # the same relabelling with indices as a replay buffer produces them (a future goal lies in the transition's own episode, at
+                # most 100 rows behind it) and an index-sorted batch (her_sample_indices): near-sequential gathers instead of random sectors
+                gen2 = torch.Generator(device=dev).manual_seed(99)
+                for lab2, srt in (("episode_local_goals_unsorted_batch", False), ("episode_local_goals_index_sorted_batch", True)):
+                    s2, g2 = p.her_sample_indices(R, M, 100, 0.8, device=dev, generator=gen2, sort=srt)
+                    for _ in range(3):
+                        p.her_relabel("stack", "sparse", nag[:, :G], dgb[:, :G], s2, g2)
+                    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                    for a, b in evs:
+                        flush.zero_()
+                        a.record(); p.her_relabel("stack", "sparse", nag[:, :G], dgb[:, :G], s2, g2); b.record()
+                    torch.cuda.synchronize(dev)
+                    ms2 = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+                    t0s = time.perf_counter(); torch.sort(s2); torch.cuda.synchronize(dev); sort_ms = (time.perf_counter() - t0s) * 1e3
+                    her[f"her_relabel_1M_of_16M_rows_6d_dense_24B_rows_{lab2}"] = {
+                        "transitions_per_s": M / (ms2 / 1e3), "ms": ms2, "achieved_gbs": nbytes / (ms2 / 1e3) / 1e9, "bytes_per_transition": 16 + 3 * G * 4 + 4,
+                        "note": "algorithmic bytes; torch.sort of the 1 M sampled indices (outside the timed region) took %.3f ms wall" % sort_ms}
             del nag, dgb
         del src, gs
     if rank == 0:
@@ -345,6 +363,21 @@ def run_gpu(args):
                 v["frac_of_measured_hbm"] = v["achieved_gbs"] / peak
                 if "achieved_gbs_in_sector_terms" in v:
                     v["frac_of_measured_hbm_in_sector_terms"] = v["achieved_gbs_in_sector_terms"] / peak
+            # what DRAM really moved for these kernels (ncu dram__bytes, profiles/her_kernel_traffic.json written by scripts/her_traffic.py): a random
+            # 24-byte row gather costs one or two 64-byte DRAM accesses, so the gather kernel is HBM-bound at a small algorithmic fraction
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "her_kernel_traffic.json")))
+                match = {"stack_1M_rows_6d": "stack_1M_rows_6d", "reach_32M_rows_3d": "reach_32M_rows_3d", "dense_24B_rows (": "her_relabel_random_indices",
+                         "unsorted_batch": "her_relabel_episode_local_goals_unsorted_batch", "index_sorted_batch": "her_relabel_episode_local_goals_index_sorted_batch"}
+                for name, v in her.items():
+                    for frag, key in match.items():
+                        if frag in name and key in traffic:
+                            t = traffic[key]
+                            v["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                            v["frac_of_measured_hbm_by_dram_traffic"] = v["traffic"] / (v["ms"] / 1e3) / 1e9 / peak
+                            v["traffic_source"] = t["source"]
+            except Exception:
+                pass
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             lib = oracle_lib()

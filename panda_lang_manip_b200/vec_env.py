@@ -375,3 +375,21 @@ def future_goal_indices(episode_start: torch.Tensor, episode_length: torch.Tenso
     fut = src + (u * span).long().clamp_max(span - 1)
     keep = torch.rand(src.shape, device=src.device, generator=generator) >= her_ratio
     return torch.where(keep, torch.full_like(fut, -1), fut)
+
+
+def her_sample_indices(num_rows: int, batch: int, episode_length: int, her_ratio: float = 0.8, device=None,
+                       generator: Optional[torch.Generator] = None, sort: bool = True):
+    """Sampled transitions and their "future" goal rows for ``her_relabel`` on a replay buffer whose episodes are stored back to back
+    (``episode_length`` rows each, as stable-baselines3's HerReplayBuffer lays them out per env): returns ``(src, goal_src)``.
+    With ``sort=True`` (default) ``src`` is ascending: a batch is a set, so its order is free, and an index-sorted batch turns the two
+    random row gathers into near-sequential ones -- the sampled rows are ~num_rows / batch apart and a transition's future goal lies at
+    most ``episode_length`` rows behind it, so consecutive threads read neighbouring DRAM pages (and sectors of the same cache lines)
+    instead of one random 32-byte sector each.  The same ``src`` then serves the observation / action gathers of the batch."""
+    device = torch.device("cuda") if device is None else device
+    src = torch.randint(0, num_rows, (batch,), device=device, generator=generator)
+    if sort:
+        src = torch.sort(src).values
+    start = (src // episode_length) * episode_length
+    length = torch.minimum(torch.full_like(src, episode_length), num_rows - start)
+    return src, future_goal_indices(start, length, src, her_ratio, generator)
+

@@ -162,3 +162,24 @@ def test_sb3_vec_env_interface():
     assert venv.get_attr("reward_type") == ["dense"] * n and venv.env_is_wrapped(object) == [False] * n
     assert venv.seed(5)[:2] == [5, 6]
     venv.close()
+
+
+@pytest.mark.gpu
+def test_index_sorted_her_batch_is_the_same_set_of_transitions():
+    """her_sample_indices(sort=True): ascending src, goals inside the transition's own episode, and the relabelled batch is what the unsorted
+    one is, row for row, after undoing the order."""
+    import torch
+    import panda_lang_manip_b200 as p
+    R, M, L = 50_000, 20_000, 50
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    src, gs = p.her_sample_indices(R, M, L, 0.8, generator=gen, sort=True)
+    assert bool((src[1:] >= src[:-1]).all())
+    fut = gs >= 0
+    assert bool(((gs[fut] >= src[fut]) & (gs[fut] // L == src[fut] // L)).all())
+    assert 0.75 < fut.float().mean().item() < 0.85
+    nag = torch.rand((R, 3), device="cuda"); dg = torch.rand((R, 3), device="cuda")
+    d1, r1 = p.her_relabel("push", "sparse", nag, dg, src, gs)
+    perm = torch.randperm(M, device="cuda")
+    d2, r2 = p.her_relabel("push", "sparse", nag, dg, src[perm], gs[perm])
+    assert torch.equal(d1[perm], d2) and torch.equal(r1[perm], r2)
+
