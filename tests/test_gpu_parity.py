@@ -118,6 +118,15 @@ def test_contact_tasks_short_horizon(task):
     assert e["compared"] == 8 * 25 and e["rew"] == 0 and e["succ"] == 0, e
 
 
+@pytest.mark.parametrize("task", ["reach", "push", "slide", "pick_and_place", "stack", "flip"])
+def test_f64_parity_mode_every_task(task):
+    """precision="f64" on every task (two-object scenes run 32-env blocks there: 416 slots x 8 B x 128 envs would not fit a block's shared
+    memory): three teacher-forced steps against the fp64 oracle -- two fp64 formulations of the same model agree to 1e-6 (measured 2e-7 at worst: the
+    sweep loop's exit test is a discontinuity that two formulations cross at slightly different residuals)."""
+    e = _rollout(task, "ee", n_envs=4, steps=3, precision="f64", seed=6, teacher=True)
+    assert e["q"] < 1e-6 and e["ee"] < 1e-6 and e["obj"] < 1e-6 and e["compared"] == 4 * 3 and e["rew"] == 0 and e["succ"] == 0, e
+
+
 @pytest.mark.parametrize("task", ["push", "pick_and_place", "stack"])
 def test_contact_tasks_per_step(task):
     """Per-step (teacher-forced) agreement on contact tasks: robot 1e-4, object pose (position, quaternion) 5e-4."""
