@@ -75,6 +75,7 @@ template <typename T> PG_HD V3<T> obj_vertex(const Scene<T>& S, int o, int k) {
     int a = k & 3;
     return mk<T>((a == 0 || a == 3) ? c : -c, (a < 2) ? c : -c, (k & 4) ? S.half[o][2] : -S.half[o][2]);
 }
+// edge e (0..11) of a box in the world: axis e / 4, the two other coordinates at -+ half by the bits of e; start point p, direction d (full length)
 template <typename T> PG_HD T sdf_box(const T* h, V3<T> p, V3<T>& n, bool& face) {
     face = true;
     T dx = fabs(p.x) - h[0], dy = fabs(p.y) - h[1], dz = fabs(p.z) - h[2];
@@ -101,6 +102,14 @@ template <typename T> PG_HD T sdf_cyl(T r, T hz, V3<T> p, V3<T>& n, bool& face) 
     T a = dr > 0 ? dr : T(0), b = dz > 0 ? dz : T(0), len = sqrt(a * a + b * b);
     n = mk<T>(rx * a / len, ry * a / len, sz * b / len);
     return len;
+}
+template <typename T> PG_HD void box_edge(const T* h, const Rot<T>& R, V3<T> pos, int e, V3<T>& p, V3<T>& d) {
+    const int a = e >> 2, b1 = (a + 1) % 3, c1 = (a + 2) % 3;
+    T l[3];
+    l[a] = -h[a]; l[b1] = (e & 1) ? h[b1] : -h[b1]; l[c1] = (e & 2) ? h[c1] : -h[c1];
+    p = rot_mul(R, mk<T>(l[0], l[1], l[2])) + pos;
+    const V3<T> ax = a == 0 ? R.X : (a == 1 ? R.Y : R.Z);
+    d = ax * (T(2) * h[a]);
 }
 template <typename T> PG_HD T obj_sdf(const Scene<T>& S, int o, V3<T> p, V3<T>& n, bool& face) {
     return S.shape[o] == SH_BOX ? sdf_box(S.half[o], p, n, face) : sdf_cyl(S.half[o][0], S.half[o][2], p, n, face);
@@ -256,11 +265,70 @@ PG_HD void collect_contacts(const Scene<T>& S, const World<T, NOBJ>& W, const Ob
 #pragma unroll
             for (int a = 0; a < 2; a++) {
                 const int b = 1 - a;
+                const int ia = NOBJ == 2 ? a : 0, ib = NOBJ == 2 ? b : 0;
+                if (S.shape[a] == SH_BOX && S.shape[b] == SH_BOX) {
+                    // 4a. box <-> box, vertices of A against B's REFERENCE FACE: the face axis of B along which the two boxes overlap least (the
+                    // separating-axis choice of Bullet's box-box detector restricted to B's face normals); a vertex within the margin of that
+                    // face's plane and inside the face's rectangle grown by the margin is a contact along the face normal.  B's signed-distance
+                    // field alone cannot make this choice: a vertex of a cube stacked on a cube of the same size sits at a corner of the
+                    // other's face, where the nearest face is a side face as often as the top (the oracle's "4a").
+                    const Rot<T>& Ra = W.Ro[ia]; const Rot<T>& Rbm = W.Ro[ib];
+                    const V3<T> cl = rot_tmul(Rbm, ob[ia].pos - ob[ib].pos);
+                    const V3<T> Bx[3] = {Rbm.X, Rbm.Y, Rbm.Z}, Ax[3] = {Ra.X, Ra.Y, Ra.Z};
+                    const T clv[3] = {cl.x, cl.y, cl.z};
+                    T depth[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        T proj = T(0);
+#pragma unroll
+                        for (int j = 0; j < 3; j++) proj += fabs(dot(Bx[k], Ax[j])) * S.half[a][j];
+                        depth[k] = S.half[b][k] + proj - fabs(clv[k]);
+                    }
+                    int km = 0; if (depth[1] < depth[km]) km = 1; if (depth[2] < depth[km]) km = 2;
+                    if (depth[km] < -S.margin) continue;            // separated along that axis
+                    const T sg = clv[km] >= T(0) ? T(1) : T(-1);
+                    const V3<T> nw = Bx[km] * sg;
+                    const int i1 = (km + 1) % 3, i2 = (km + 2) % 3;
+                    for (int k = 0; k < 8; k++) {
+                        const V3<T> P = rot_mul(Ra, box_vertex(S.half[a], k)) + ob[ia].pos;
+                        const V3<T> pl = rot_tmul(Rbm, P - ob[ib].pos);
+                        const T plv[3] = {pl.x, pl.y, pl.z};
+                        const T d = sg * plv[km] - S.half[b][km];
+                        if (d < S.margin && d > T(-0.01) && fabs(plv[i1]) <= S.half[b][i1] + S.margin && fabs(plv[i2]) <= S.half[b][i2] + S.margin)
+                            add_contact(C, P, nw, d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
+                    }
+                    continue;
+                }
                 for (int k = 0; k < 8; k++) {
                     V3<T> P = rot_mul(W.Ro[(NOBJ == 2 ? a : 0)], obj_vertex(S, a, k)) + ob[(NOBJ == 2 ? a : 0)].pos;
                     V3<T> nl, pl = rot_tmul(W.Ro[(NOBJ == 2 ? b : 0)], P - ob[(NOBJ == 2 ? b : 0)].pos);
                     bool face; T d = obj_sdf(S, b, pl, nl, face);
                     if (d < S.margin) add_contact(C, P, rot_mul(W.Ro[(NOBJ == 2 ? b : 0)], nl), d, 3 + a, 3 + b, S.mu[a] * S.mu[b], false);
+                }
+            }
+            // 4b. box <-> box, edge against edge: two boxes whose faces overlap with every vertex of either outside the other's face (a cube
+            // lying rotated on a cube of the same size: tasks/stack.py:30-62) have no vertex-in-field contact.  Every pair of edges whose
+            // mutual closest points are interior to both edges and closer than the margin is a contact along the edges' common
+            // perpendicular, pointing from object 1 to object 0 (the oracle's "4b", same enumeration order).
+            if (S.shape[0] == SH_BOX && S.shape[NOBJ - 1] == SH_BOX) {
+                const V3<T> dc = ob[0].pos - ob[NOBJ - 1].pos;
+#pragma unroll 1
+                for (int ea = 0; ea < 12; ea++) {
+                    V3<T> p1, d1; box_edge(S.half[0], W.Ro[0], ob[0].pos, ea, p1, d1);
+#pragma unroll 1
+                    for (int eb = 0; eb < 12; eb++) {
+                        V3<T> p2, d2; box_edge(S.half[NOBJ - 1], W.Ro[NOBJ - 1], ob[NOBJ - 1].pos, eb, p2, d2);
+                        const V3<T> r = p1 - p2;
+                        const T A = dot(d1, d1), E = dot(d2, d2), B = dot(d1, d2), Cc = dot(d1, r), F = dot(d2, r), den = A * E - B * B;
+                        if (den <= T(0.01) * A * E) continue;                      // (nearly) parallel edges
+                        const T sa = (B * F - Cc * E) / den, tb = (A * F - B * Cc) / den;
+                        if (sa <= T(0.02) || sa >= T(0.98) || tb <= T(0.02) || tb >= T(0.98)) continue;     // an end point is closest: a vertex contact's business
+                        V3<T> n = cross(d1, d2) * (T(1) / sqrt(den));
+                        if (dot(n, dc) < T(0)) n = n * T(-1);
+                        const V3<T> pa = p1 + d1 * sa, pb = p2 + d2 * tb;
+                        const T d = dot(pa - pb, n);
+                        if (d < S.margin && d > T(-0.01)) add_contact(C, (pa + pb) * T(0.5), n, d, 3, 3 + NOBJ - 1, S.mu[0] * S.mu[NOBJ - 1], false);
+                    }
                 }
             }
         }

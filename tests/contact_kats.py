@@ -11,8 +11,10 @@ NEUTRAL = np.array([0.0, 0.41, 0.0, -1.85, 0.0, 2.26, 0.79, 0.0, 0.0])
 def state_row(task, objs, goal):
     """q(9) qd(9) | objects pos3 quat4 lin3 ang3 | goal: robot at the neutral pose (gripper 20 cm above the table, out of the way)."""
     row = [NEUTRAL, np.zeros(9)]
-    for pos, vel in objs:
-        row += [np.asarray(pos, float), [0, 0, 0, 1], np.asarray(vel, float), [0, 0, 0]]
+    for o in objs:
+        pos, vel = o[0], o[1]
+        quat = o[2] if len(o) > 2 else [0, 0, 0, 1]
+        row += [np.asarray(pos, float), np.asarray(quat, float), np.asarray(vel, float), [0, 0, 0]]
     row.append(np.asarray(goal, float))
     return np.concatenate([np.asarray(r, float) for r in row])
 
@@ -71,6 +73,28 @@ def run_all(make_runner):
     out["puck_velocity"] = (st[25], v_want, 0.01 * v_want)
     out["puck_distance"] = (st[18], x_want, 0.01 * x_want)
     out["puck_height"] = (st[20], 0.015, 2e-4)
+    r.close()
+    # 5. Stack (tasks/stack.py:30-62: a 2 kg and a 1 kg 4 cm cube): the second cube resting on the first stays there -- exactly aligned (every
+    # vertex at a corner of the other cube's face: the reference-face rule decides the normal), shifted, and turned by 20 / 45 degrees about
+    # z, where every vertex of either cube lies outside the other's face and only the edge-against-edge contacts carry it (8 crossings of
+    # the two squares); a cube whose centre of mass overhangs the lower cube's edge (25 mm of 20) tips off and ends up on the table
+    r = make_runner("stack")
+    zero8 = np.zeros(8, np.float32)
+    for name, ang, off in (("exactly_aligned", 0.0, 0.0), ("shifted_2mm", 0.0, 0.002), ("turned_45_deg", np.pi / 4, 0.002), ("turned_20_deg", np.radians(20.0), 0.0005)):
+        quat = [0, 0, np.sin(ang / 2), np.cos(ang / 2)]
+        r.set(state_row("stack", [([0.1, 0.05, 0.02], [0, 0, 0]), ([0.1 + off, 0.05 + off / 2, 0.06], [0, 0, 0], quat)], [0.1, 0.05, 0.02, 0.1, 0.05, 0.06]))
+        for _ in range(25):
+            st = r.step(zero8)
+        out[f"stacked_{name}_upper_height"] = (st[33], 0.06, 3e-4)
+        out[f"stacked_{name}_lower_height"] = (st[20], 0.02, 3e-4)
+        out[f"stacked_{name}_upper_drift_xy"] = (float(np.abs(st[31:33] - [0.1 + off, 0.05 + off / 2]).max()), 0.0, 3e-4)
+        out[f"stacked_{name}_upper_speed"] = (float(np.abs(st[38:44]).max()), 0.0, 5e-3)
+        out[f"stacked_{name}_upper_keeps_its_yaw"] = (float(abs(st[37]) - np.cos(ang / 2)), 0.0, 1e-3)
+    r.set(state_row("stack", [([0.1, 0.05, 0.02], [0, 0, 0]), ([0.125, 0.05, 0.06], [0, 0, 0])], [0.1, 0.05, 0.02, 0.1, 0.05, 0.06]))
+    for _ in range(40):
+        st = r.step(zero8)
+    out["overhanging_cube_falls_to_the_table"] = (st[33], 0.02, 1e-3)
+    out["overhanging_cube_leaves_the_lower_one_in_place"] = (float(np.abs(st[18:20] - [0.1, 0.05]).max()), 0.0, 2e-3)
     r.close()
     return out
 

@@ -99,3 +99,25 @@ def test_mass_matrix_inverse(hostcheck, oracle):
         hostcheck.hc_minv(1, P(BASE), P(np.ascontiguousarray(q)), P(np.ascontiguousarray(qd)), P(mh), P(qdd))
         assert np.abs(mh - mo).max() / np.abs(mo).max() < 1e-12
     oe.close()
+
+
+@pytest.mark.parametrize("deg,off", [(0.0, 0.0), (3.0, 0.0005), (20.0, 0.002), (45.0, 0.0), (12.0, 0.015)])
+def test_box_on_box_contacts_match_the_oracle(hostcheck, deg, off):
+    """Stack with the second cube lying on the first, turned / shifted: the kernel math's box-box contacts (vertices against the reference
+    face, edge against edge) against the oracle's, fp64, 10 env steps of a resting stack -- and the stack stays up."""
+    from tests.contact_kats import state_row
+    ang = np.radians(deg)
+    row = state_row("stack", [([0.1, 0.05, 0.02], [0, 0, 0]), ([0.1 + off, 0.05 - off / 2, 0.06], [0, 0, 0], [0, 0, np.sin(ang / 2), np.cos(ang / 2)])],
+                    [0.1, 0.05, 0.02, 0.1, 0.05, 0.06])
+    oe = OracleEnv("stack", "joints"); oe.set_full_state(row)
+    st = np.zeros(50); st[:44] = row[:44]; st[44:] = row[44:50]
+    a = np.zeros(8, np.float32)
+    for t in range(10):
+        oe.step(a)
+        o2, a2, d2 = np.zeros(OBS_DIM["stack"], np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32)
+        r2, s2 = np.zeros(1, np.float32), np.zeros(1, np.uint8)
+        hostcheck.hc_env_step(1, TASK_ID["stack"], 1, 0, P(BASE), P(st), P(a), P(o2), P(a2), P(d2), P(r2), P(s2))
+        ref = oe.full_state()
+        assert np.abs(st[:44] - ref[:44]).max() < 1e-7, (t, np.abs(st[:44] - ref[:44]).max())
+    oe.close()
+    assert abs(st[33] - 0.06) < 3e-4 and abs(st[20] - 0.02) < 3e-4
