@@ -508,7 +508,8 @@ void po_inverse_kinematics(const PoSim *s, int link, const double pos[3], const 
  *   a contact = a vertex of body A against the signed-distance field of body B (plane / box / cylinder) with
  *   distance < CONTACT_MARGIN (4 mm: twice the largest per-sub-step approach, instead of Bullet's 2 cm breaking threshold,
  *   to bound the row count); at most MAXC_* contacts in collection order; pairs: object-table(+ground plane), robot box-table, robot box<->object (both
- *   directions), object<->object (both directions).
+ *   directions), object<->object (both directions); box<->box object pairs use the other box's REFERENCE FACE (the face axis of minimum overlap)
+ *   instead of its distance field for the vertex contacts and add edge-against-edge contacts (see 4a / 4b in collect_contacts).
  * Rows follow btMultiBodyConstraintSolver::setupMultiBodyContactConstraint: speculative when distance > 0
  * (velocityError -= distance/dt), erp 0.2 when penetrating, friction = product of the two coefficients, two friction
  * directions from btPlaneSpace1 with the implicit cone clamp, finger links soft (stiffness 30000, damping 1000 ->

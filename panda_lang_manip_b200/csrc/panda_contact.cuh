@@ -5,8 +5,9 @@
 // _create_scene; friction: panda_gym/envs/robots/panda.py:47-50, slide.py:34-42).
 //
 // Contact model (defined by oracle/panda_oracle.c, "contact model"): vertices of one body against the signed-distance
-// field of the other (table plane, box, z-cylinder), speculative rows inside a 4 mm margin, two friction directions with an
-// implicit cone, soft finger contacts, sequential impulses interleaved with the joint-limit and motor rows.
+// field of the other (table plane, box, z-cylinder; box <-> box object pairs: vertices against the other box's reference face plus
+// edge against edge), speculative rows inside a 4 mm margin, two friction directions with an implicit cone, soft finger contacts,
+// sequential impulses interleaved with the joint-limit and motor rows.
 // Contact records (geometry + 3 x (1/D, rhs, impulse)) and the operational-space Jacobian live in shared memory, word-interleaved
 // by thread; the robot part of a row is a wrench in the gripper's 8-dimensional operational space, the free-body part is
 // recomputed from the contact geometry each sweep (see "contact storage" below).
