@@ -63,6 +63,16 @@ def run_all(make_runner):
     out["cube_slide_distance"] = (st[18] + 0.1, x_want, 0.03 * x_want)
     out["cube_slide_stops"] = (float(np.abs(st[25:28]).max()), 0.0, 2e-3)
     out["cube_slide_straight"] = (float(abs(st[19])), 0.0, 1e-3)
+    # 3b. a cube dropped tilted about x lands on an edge and settles on the nearer face: 30 degrees falls back flat, 60 degrees rolls on to
+    # the next face (quaternion (sin 45, 0, 0, cos 45)); either way it ends at rest at the half-size height
+    for name, deg, qx in (("30", 30.0, 0.0), ("60", 60.0, np.sin(np.pi / 4))):
+        ang = np.radians(deg)
+        r.set(state_row("push", [([0.1, 0.05, 0.07], [0, 0, 0], [np.sin(ang / 2), 0, 0, np.cos(ang / 2)])], [0, 0, 0.02]))
+        for _ in range(50):
+            st = r.step(zero7)
+        out[f"tilted_{name}_deg_drop_settles_height"] = (st[20], 0.02, 3e-4)
+        out[f"tilted_{name}_deg_drop_settles_speed"] = (float(np.abs(st[25:31]).max()), 0.0, 3e-3)
+        out[f"tilted_{name}_deg_drop_ends_on_a_face"] = (float(abs(st[21])), qx, 2e-3)
     r.close()
     # 4. the Slide puck (lateral friction 0.04 x table 0.5 = 0.02) decelerates at mu g: velocity after 10 env steps
     r = make_runner("slide")
@@ -73,6 +83,24 @@ def run_all(make_runner):
     out["puck_velocity"] = (st[25], v_want, 0.01 * v_want)
     out["puck_distance"] = (st[18], x_want, 0.01 * x_want)
     out["puck_height"] = (st[20], 0.015, 2e-4)
+    r.close()
+    # 4b. PickAndPlace: the 1 kg cube between the closed fingers of the arm at its neutral pose (grasp target at (0.0384, 0, 0.1974), 18 cm above
+    # the table) is held against gravity by friction alone (finger 1.0 x cube 0.5, 20 N per finger from the position motors: 20 N > m g) while
+    # the gripper keeps closing, and drops when the gripper opens
+    r = make_runner("pick_and_place")
+    row = state_row("pick_and_place", [([0.0384, 0.0, 0.1974], [0, 0, 0])], [0, 0, 0.1])
+    row[7] = row[8] = 0.0205
+    r.set(row)
+    act = np.zeros(8, np.float32); act[7] = -1.0
+    for _ in range(30):
+        st = r.step(act)
+    out["grasped_cube_is_held_height"] = (st[20], 0.1974, 1e-3)
+    out["grasped_cube_is_held_xy"] = (float(np.abs(st[18:20] - [0.0384, 0.0]).max()), 0.0, 1e-3)
+    out["grasped_cube_is_held_speed"] = (float(np.abs(st[25:28]).max()), 0.0, 5e-3)
+    act[7] = 1.0
+    for _ in range(25):
+        st = r.step(act)
+    out["released_cube_lands_on_the_table"] = (st[20], 0.02, 1e-3)
     r.close()
     # 5. Stack (tasks/stack.py:30-62: a 2 kg and a 1 kg 4 cm cube): the second cube resting on the first stays there -- exactly aligned (every
     # vertex at a corner of the other cube's face: the reference-face rule decides the normal), shifted, and turned by 20 / 45 degrees about
