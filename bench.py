@@ -327,6 +327,27 @@ def run_gpu(args):
                         "note": "algorithmic bytes; torch.sort of the 1 M sampled indices (outside the timed region) took %.3f ms wall" % sort_ms}
             del nag, dgb
         del src, gs
+    # analytic depth / point-cloud renderer: 256 PickAndPlace envs x the reference's 480 x 480 camera (pybullet.py:149-160),
+    # depth + colour + deprojected points + validity = 21 B written per pixel
+    render = None
+    if rank == 0 and not args.no_her:
+        try:
+            renv = p.PandaVecEnv("pick_and_place", 256, control_type="ee", device=local)
+            for _ in range(2):
+                out = renv.render(width=480, height=480)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            for a, b in evs:
+                flush.zero_()
+                a.record(); out = renv.render(width=480, height=480); b.record()
+            torch.cuda.synchronize(dev)
+            ms = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+            npix = 256 * 480 * 480
+            render = {"workload": "256 envs x 480 x 480, depth + rgba + points + valid", "ms": ms, "pixels_per_s": npix / (ms / 1e3), "bytes_per_pixel": 21,
+                      "achieved_gbs": npix * 21 / (ms / 1e3) / 1e9, "valid_fraction": float(out["valid"].float().mean().item()),
+                      "note": "includes the output allocations of PandaVecEnv.render and the per-env primitive set-up launch"}
+            renv.close(); del out
+        except Exception as exc:
+            render = {"error": repr(exc)}
     if rank == 0:
         peaks = {}
         try:
@@ -353,11 +374,14 @@ def run_gpu(args):
                          "note": "latency/issue-bound kernel (~1 MFLOP of serial dynamics per env-step): the HBM fraction is structurally tiny, see DESIGN.md"},
             "also": also,
             "her_compute_reward": her,
+            "render": render,
             "clocks": clocks,
             "wall_s_timed_leg": t_wall,
             "episode_stats": {"diverged_env_steps": diverged, "contact_candidates_dropped_at_cap": overflows, "episodes": stats[0].item(), "success_rate": (stats[1] / stats[0]).item() if stats[0].item() > 0 else None,
                               "mean_return": (stats[2] / stats[0]).item() if stats[0].item() > 0 else None},
         }
+        if render and "achieved_gbs" in render:
+            render["frac_of_measured_hbm"] = render["achieved_gbs"] / peak
         if her:
             for v in her.values():
                 v["frac_of_measured_hbm"] = v["achieved_gbs"] / peak

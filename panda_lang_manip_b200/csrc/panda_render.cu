@@ -6,8 +6,10 @@
 // the robot's visual meshes with OpenGL; those meshes are not part of /root/reference, so the robot is drawn as the boxes the physics
 // uses (arm links: the inertia AABBs of panda_model.h; hand and fingers: the collision boxes of panda_scene.h) -- "primitives only".
 //
-// One thread per pixel, rays cast against <= 16 oriented boxes / z-cylinders held in shared memory (built once per env by
-// render_setup_kernel), everything a pixel produces is written once: 22 B per pixel -> HBM-write bound.
+// One thread per pixel, 16 x 16 pixel tiles; a tile culls the env's <= 16 oriented boxes / z-cylinders (built once per env by
+// render_setup_kernel) to those whose screen rectangle touches it, rays are cast against that short list from shared memory and
+// everything a pixel produces is written once (21-22 B per pixel).  Round-2 ncu: the un-culled version was instruction-bound
+// (2,330 instructions per pixel, 4.2 ms for 256 x 480 x 480), not write-bound.
 #include <cuda_runtime.h>
 #include <math.h>
 #include "panda_kernels.cuh"
@@ -58,14 +60,13 @@ __global__ void __launch_bounds__(BLOCK) render_setup_kernel(const __grid_consta
 }
 
 // slab test in the primitive's frame; returns the entry distance (ray parameter; dir has unit forward component, so it IS the eye depth)
-__device__ __forceinline__ float hit_box(const RenderPrim& p, const float* o, const float* d, float* nrm) {
-    const float rel[3] = {o[0] - p.c[0], o[1] - p.c[1], o[2] - p.c[2]};
-    const float lo[3] = {rel[0] * p.X[0] + rel[1] * p.X[1] + rel[2] * p.X[2], rel[0] * p.Y[0] + rel[1] * p.Y[1] + rel[2] * p.Y[2], rel[0] * p.Z[0] + rel[1] * p.Z[1] + rel[2] * p.Z[2]};
+// lo: the eye in the primitive's frame (the same for every pixel of a tile: computed once per tile and primitive)
+__device__ __forceinline__ float hit_box(const RenderPrim& p, const float* lo, const float* d, float* nrm) {
     const float ld[3] = {d[0] * p.X[0] + d[1] * p.X[1] + d[2] * p.X[2], d[0] * p.Y[0] + d[1] * p.Y[1] + d[2] * p.Y[2], d[0] * p.Z[0] + d[1] * p.Z[1] + d[2] * p.Z[2]};
     float t0 = -1e30f, t1 = 1e30f; int ax = 0; float sg = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float inv = 1.0f / ld[k];                         // +-inf for an axis-parallel ray: the comparisons below still order correctly
+        const float inv = __fdividef(1.0f, ld[k]);             // MUFU.RCP (1 ulp; the IEEE division is ~8 instructions, three per primitive and pixel); +-inf for an axis-parallel ray
         float a = (-p.h[k] - lo[k]) * inv, b = (p.h[k] - lo[k]) * inv;
         if (ld[k] == 0.f) { if (fabsf(lo[k]) > p.h[k]) return -1.f; a = -1e30f; b = 1e30f; }
         const float near = fminf(a, b), far = fmaxf(a, b);
@@ -77,9 +78,7 @@ __device__ __forceinline__ float hit_box(const RenderPrim& p, const float* o, co
     nrm[0] = sg * A[0]; nrm[1] = sg * A[1]; nrm[2] = sg * A[2];
     return t0;
 }
-__device__ __forceinline__ float hit_cyl(const RenderPrim& p, const float* o, const float* d, float* nrm) {       // z-cylinder: radius h[0], half height h[2]
-    const float rel[3] = {o[0] - p.c[0], o[1] - p.c[1], o[2] - p.c[2]};
-    const float lo[3] = {rel[0] * p.X[0] + rel[1] * p.X[1] + rel[2] * p.X[2], rel[0] * p.Y[0] + rel[1] * p.Y[1] + rel[2] * p.Y[2], rel[0] * p.Z[0] + rel[1] * p.Z[1] + rel[2] * p.Z[2]};
+__device__ __forceinline__ float hit_cyl(const RenderPrim& p, const float* lo, const float* d, float* nrm) {       // z-cylinder: radius h[0], half height h[2]
     const float ld[3] = {d[0] * p.X[0] + d[1] * p.X[1] + d[2] * p.X[2], d[0] * p.Y[0] + d[1] * p.Y[1] + d[2] * p.Y[2], d[0] * p.Z[0] + d[1] * p.Z[1] + d[2] * p.Z[2]};
     const float r = p.h[0], hz = p.h[2];
     float best = -1.f;
@@ -103,47 +102,95 @@ __device__ __forceinline__ float hit_cyl(const RenderPrim& p, const float* o, co
     return best;
 }
 
-__global__ void __launch_bounds__(256) render_kernel(const RenderPrim* __restrict__ prims, const RenderCamera C, float* __restrict__ depth, uchar4* __restrict__ rgba,
-                                                     unsigned char* __restrict__ seg, float* __restrict__ points, unsigned char* __restrict__ valid) {
+// One block = one 16 x 16 pixel tile of one env.  The tile first culls the env's primitive list: thread (k, c) projects corner c of
+// primitive k's bounding box, a primitive stays in the tile's list when its screen rectangle (grown by a pixel) overlaps the tile or a
+// corner lies at / behind the eye plane (conservative) -- a pixel then tests 1-4 primitives instead of up to 16, which is what the
+// kernel's time went into (ncu, round 2: 87 % issue-active, 2,330 instructions per pixel before the culling).  Order of the list is
+// kept, so ties resolve as without it.  The deprojected points (3 floats per pixel) leave through shared memory as contiguous runs.
+constexpr int RT = 16;      // tile edge
+__global__ void __launch_bounds__(RT * RT) render_kernel(const RenderPrim* __restrict__ prims, const RenderCamera C, float* __restrict__ depth, uchar4* __restrict__ rgba,
+                                                         unsigned char* __restrict__ seg, float* __restrict__ points, unsigned char* __restrict__ valid) {
     __shared__ RenderPrim s_p[RENDER_MAX_PRIMS];
-    const int env = blockIdx.y;
+    __shared__ int s_lo[RENDER_MAX_PRIMS][2], s_hi[RENDER_MAX_PRIMS][2], s_behind[RENDER_MAX_PRIMS], s_list[RENDER_MAX_PRIMS], s_n;
+    __shared__ float s_pts[RT * RT * 3], s_eye[RENDER_MAX_PRIMS][3];
+    const int env = blockIdx.z, tid = threadIdx.x;
     {   // the env's primitive list: RENDER_MAX_PRIMS x 24 words, loaded cooperatively
         const int words = RENDER_MAX_PRIMS * (int)(sizeof(RenderPrim) / 4);
         const int* src = reinterpret_cast<const int*>(prims + (size_t)env * RENDER_MAX_PRIMS);
-        for (int k = threadIdx.x; k < words; k += 256) reinterpret_cast<int*>(s_p)[k] = src[k];
+        for (int k = tid; k < words; k += RT * RT) reinterpret_cast<int*>(s_p)[k] = src[k];
+        if (tid < RENDER_MAX_PRIMS) { s_lo[tid][0] = s_lo[tid][1] = 1 << 30; s_hi[tid][0] = s_hi[tid][1] = -(1 << 30); s_behind[tid] = 0; }
     }
     __syncthreads();
-    const int pix = blockIdx.x * 256 + threadIdx.x, npix = C.width * C.height;
-    if (pix >= npix) return;
-    const int row = pix / C.width, col = pix - row * C.width;
+    if (tid >= RT * RT - RENDER_MAX_PRIMS) {      // the eye in each primitive's frame (the last 16 threads: the first 128 project corners)
+        const RenderPrim& p = s_p[tid - (RT * RT - RENDER_MAX_PRIMS)];
+        const float rel[3] = {C.eye[0] - p.c[0], C.eye[1] - p.c[1], C.eye[2] - p.c[2]};
+        float* e = s_eye[tid - (RT * RT - RENDER_MAX_PRIMS)];
+        e[0] = rel[0] * p.X[0] + rel[1] * p.X[1] + rel[2] * p.X[2]; e[1] = rel[0] * p.Y[0] + rel[1] * p.Y[1] + rel[2] * p.Y[2]; e[2] = rel[0] * p.Z[0] + rel[1] * p.Z[1] + rel[2] * p.Z[2];
+    }
+    if (tid < RENDER_MAX_PRIMS * 8) {   // corner c of primitive k -> pixel coordinates
+        const int k = tid >> 3, c = tid & 7;
+        const RenderPrim& p = s_p[k];
+        if (p.kind >= 0) {
+            const float sx = (c & 1) ? p.h[0] : -p.h[0], sy = (c & 2) ? p.h[1] : -p.h[1], sz = (c & 4) ? p.h[2] : -p.h[2];
+            const float v[3] = {p.c[0] + sx * p.X[0] + sy * p.Y[0] + sz * p.Z[0] - C.eye[0], p.c[1] + sx * p.X[1] + sy * p.Y[1] + sz * p.Z[1] - C.eye[1],
+                                p.c[2] + sx * p.X[2] + sy * p.Y[2] + sz * p.Z[2] - C.eye[2]};
+            const float zc = v[0] * C.fwd[0] + v[1] * C.fwd[1] + v[2] * C.fwd[2];
+            if (zc <= 1e-3f) atomicOr(&s_behind[k], 1);
+            else {
+                const float xc = v[0] * C.right[0] + v[1] * C.right[1] + v[2] * C.right[2], yc = v[0] * C.up[0] + v[1] * C.up[1] + v[2] * C.up[2];
+                const float xn = xc / (zc * C.tan_half_fov * C.aspect), yn = yc / (zc * C.tan_half_fov);
+                const float col = fminf(fmaxf((xn + 1.0f) * 0.5f * C.width, -1e6f), 1e6f), row = fminf(fmaxf((1.0f - yn) * 0.5f * C.height, -1e6f), 1e6f);
+                atomicMin(&s_lo[k][0], (int)floorf(col) - 1); atomicMax(&s_hi[k][0], (int)ceilf(col) + 1);
+                atomicMin(&s_lo[k][1], (int)floorf(row) - 1); atomicMax(&s_hi[k][1], (int)ceilf(row) + 1);
+            }
+        }
+    }
+    __syncthreads();
+    const int x0 = blockIdx.x * RT, y0 = blockIdx.y * RT;
+    if (tid < 32) {     // ordered compaction by the first warp: lane k decides primitive k
+        bool in = false;
+        if (tid < RENDER_MAX_PRIMS && s_p[tid].kind >= 0)
+            in = s_behind[tid] || (s_lo[tid][0] <= x0 + RT - 1 && s_hi[tid][0] >= x0 && s_lo[tid][1] <= y0 + RT - 1 && s_hi[tid][1] >= y0);
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (in) s_list[__popc(m & ((1u << tid) - 1u))] = tid;
+        if (tid == 0) s_n = __popc(m);
+    }
+    __syncthreads();
+    const int col = x0 + (tid & (RT - 1)), row = y0 + (tid >> 4), npix = C.width * C.height;
+    const bool inside = col < C.width && row < C.height;
+    float best = 1e30f, bn[3] = {0.f, 0.f, 1.f}; int id = 0;
     // ray through the pixel centre; dir = forward + x right + y up, unit forward component
     const float xn = (col + 0.5f) * (2.0f / C.width) - 1.0f, yn = 1.0f - (row + 0.5f) * (2.0f / C.height);
     const float dx = xn * C.tan_half_fov * C.aspect, dy = yn * C.tan_half_fov;
     const float d[3] = {C.fwd[0] + dx * C.right[0] + dy * C.up[0], C.fwd[1] + dx * C.right[1] + dy * C.up[1], C.fwd[2] + dx * C.right[2] + dy * C.up[2]};
-    float best = 1e30f, bn[3] = {0.f, 0.f, 1.f}; int id = 0;
+    if (inside) {
+        const int n = s_n;
 #pragma unroll 1
-    for (int k = 0; k < RENDER_MAX_PRIMS; k++) {
-        const RenderPrim& p = s_p[k];
-        if (p.kind < 0) break;
-        float nrm[3];
-        const float t = p.kind == 0 ? hit_box(p, C.eye, d, nrm) : hit_cyl(p, C.eye, d, nrm);
-        if (t > 0.f && t < best) { best = t; id = p.id; bn[0] = nrm[0]; bn[1] = nrm[1]; bn[2] = nrm[2]; }
+        for (int j = 0; j < n; j++) {
+            const int k = s_list[j];
+            const RenderPrim& p = s_p[k];
+            float nrm[3];
+            const float t = p.kind == 0 ? hit_box(p, s_eye[k], d, nrm) : hit_cyl(p, s_eye[k], d, nrm);
+            if (t > 0.f && t < best) { best = t; id = p.id; bn[0] = nrm[0]; bn[1] = nrm[1]; bn[2] = nrm[2]; }
+        }
     }
     const bool hit = best >= C.near && best <= C.far;
     // OpenGL depth buffer value of the eye depth (what getCameraImage returns): z_ndc = ((f + n) - 2 f n / z) / (f - n), d = (z_ndc + 1) / 2
     const float zn = hit ? ((C.far + C.near) - 2.0f * C.far * C.near / best) / (C.far - C.near) : 1.0f;
     const float db = hit ? 0.5f * (zn + 1.0f) : 1.0f;
-    const size_t g = (size_t)env * npix + pix;
-    if (depth) depth[g] = db;
-    if (seg) seg[g] = hit ? (unsigned char)id : 0;
-    if (rgba) {
-        uchar4 c = make_uchar4(C.background[0], C.background[1], C.background[2], 255);
-        if (hit) {
-            const unsigned char* base = C.color[id < RENDER_ID_ROBOT ? id : RENDER_ID_ROBOT];
-            const float sh = 0.45f + 0.55f * fmaxf(0.f, bn[0] * C.light[0] + bn[1] * C.light[1] + bn[2] * C.light[2]);
-            c = make_uchar4((unsigned char)(base[0] * sh), (unsigned char)(base[1] * sh), (unsigned char)(base[2] * sh), 255);
+    const size_t g = (size_t)env * npix + (size_t)row * C.width + col;
+    if (inside) {
+        if (depth) depth[g] = db;
+        if (seg) seg[g] = hit ? (unsigned char)id : 0;
+        if (rgba) {
+            uchar4 c = make_uchar4(C.background[0], C.background[1], C.background[2], 255);
+            if (hit) {
+                const unsigned char* base = C.color[id < RENDER_ID_ROBOT ? id : RENDER_ID_ROBOT];
+                const float sh = 0.45f + 0.55f * fmaxf(0.f, bn[0] * C.light[0] + bn[1] * C.light[1] + bn[2] * C.light[2]);
+                c = make_uchar4((unsigned char)(base[0] * sh), (unsigned char)(base[1] * sh), (unsigned char)(base[2] * sh), 255);
+            }
+            rgba[g] = c;
         }
-        rgba[g] = c;
     }
     if (points) {
         // the reference's deprojection (pybullet.py:213-241): NDC of the pixel CORNER (np.mgrid[-1:1:2/h, -1:1:2/w], y flipped) and of the
@@ -156,8 +203,15 @@ __global__ void __launch_bounds__(256) render_kernel(const RenderPrim* __restric
         bool ok = hit && db < 0.99f;
         if (C.crop) ok = ok && pz > 0.0f && pz < 0.67f && px > -0.5f && px < 0.2f;
         const float qnan = __int_as_float(0x7fc00000);
-        points[3 * g] = ok ? px : qnan; points[3 * g + 1] = ok ? py : qnan; points[3 * g + 2] = ok ? pz : qnan;
-        if (valid) valid[g] = ok;
+        s_pts[3 * tid] = ok ? px : qnan; s_pts[3 * tid + 1] = ok ? py : qnan; s_pts[3 * tid + 2] = ok ? pz : qnan;
+        if (valid && inside) valid[g] = ok;
+        __syncthreads();
+        // a tile row is RT pixels = 3 RT consecutive floats of the [N, H, W, 3] array
+        const int wcols = min(RT, C.width - x0);
+        for (int i = tid; i < RT * RT * 3; i += RT * RT) {
+            const int r = i / (3 * RT), o = i - r * 3 * RT;
+            if (y0 + r < C.height && o < 3 * wcols) points[((size_t)env * npix + (size_t)(y0 + r) * C.width + x0) * 3 + o] = s_pts[i];
+        }
     }
 }
 
@@ -166,9 +220,15 @@ template <typename T> void launch_render_setup(const EnvDev<T>& E, const RenderS
     g_launches++;
 }
 void launch_render(const RenderPrim* prims, const RenderCamera& C, int n_envs, float* depth, unsigned char* rgba, unsigned char* seg, float* points, unsigned char* valid, cudaStream_t st) {
-    const dim3 grid((C.width * C.height + 255) / 256, n_envs);
-    render_kernel<<<grid, 256, 0, st>>>(prims, C, depth, reinterpret_cast<uchar4*>(rgba), seg, points, valid);
-    g_launches++;
+    const size_t npix = (size_t)C.width * C.height;
+    for (int e0 = 0; e0 < n_envs; e0 += 65535) {        // gridDim.z <= 65535
+        const int ne = n_envs - e0 < 65535 ? n_envs - e0 : 65535;
+        const dim3 grid((C.width + RT - 1) / RT, (C.height + RT - 1) / RT, ne);
+        render_kernel<<<grid, RT * RT, 0, st>>>(prims + (size_t)e0 * RENDER_MAX_PRIMS, C, depth ? depth + e0 * npix : nullptr,
+                                                 rgba ? reinterpret_cast<uchar4*>(rgba) + e0 * npix : nullptr, seg ? seg + e0 * npix : nullptr,
+                                                 points ? points + 3 * e0 * npix : nullptr, valid ? valid + e0 * npix : nullptr);
+        g_launches++;
+    }
 }
 template void launch_render_setup<float>(const EnvDev<float>&, const RenderScene&, RenderPrim*, cudaStream_t);
 template void launch_render_setup<double>(const EnvDev<double>&, const RenderScene&, RenderPrim*, cudaStream_t);
