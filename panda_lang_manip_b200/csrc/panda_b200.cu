@@ -117,15 +117,25 @@ template <typename E> static int her_vector_bytes(int G, const void* a, const vo
     }
     return (int)sizeof(E);
 }
+template <typename E, int TASK, int HT> static void launch_her_ht(const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
+                                                                  long long m, long long pitch, int reward_type, double thr, cudaStream_t st) {
+    const long long per_block = 256LL * HT;
+    const int grid = (int)std::min<long long>((m + per_block - 1) / per_block, 148LL * 32);
+    const int vb = her_vector_bytes<E>(task_goal_dim(TASK), next_ag, dg, pitch);
+    if (vb == 16) her_relabel_kernel<E, TASK, 16, HT><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
+    else if (vb == 8) her_relabel_kernel<E, TASK, 8, HT><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
+    else her_relabel_kernel<E, TASK, (int)sizeof(E), HT><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
+    g_launches++;
+}
 template <typename E, int TASK> static void launch_her_task(const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
                                                             long long m, long long pitch, int reward_type, double thr, cudaStream_t st) {
-    const long long per_block = 256LL * HER_INFLIGHT;
-    const int grid = (int)std::min<long long>((m + per_block - 1) / per_block, 148LL * 16);
-    const int vb = her_vector_bytes<E>(task_goal_dim(TASK), next_ag, dg, pitch);
-    if (vb == 16) her_relabel_kernel<E, TASK, 16><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
-    else if (vb == 8) her_relabel_kernel<E, TASK, 8><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
-    else her_relabel_kernel<E, TASK, (int)sizeof(E)><<<grid, 256, 0, st>>>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr);
-    g_launches++;
+    static const int ht = [] { const char* v = getenv("PG_HER_INFLIGHT"); const int k = v ? atoi(v) : HER_INFLIGHT; return (k == 1 || k == 2 || k == 4 || k == 8) ? k : HER_INFLIGHT; }();
+    switch (ht) {
+    case 1: launch_her_ht<E, TASK, 1>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    case 2: launch_her_ht<E, TASK, 2>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    case 8: launch_her_ht<E, TASK, 8>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    default: launch_her_ht<E, TASK, 4>(next_ag, dg, src, goal_src, dg_out, ag_out, reward, m, pitch, reward_type, thr, st); break;
+    }
 }
 template <typename E> static void launch_her(int task, const E* next_ag, const E* dg, const long long* src, const long long* goal_src, E* dg_out, E* ag_out, float* reward,
                                              long long m, long long pitch, int reward_type, double thr, cudaStream_t st) {

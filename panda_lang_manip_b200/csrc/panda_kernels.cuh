@@ -574,12 +574,12 @@ template <typename E, int G, int VB> struct RowLoad {
         }
     }
 };
-constexpr int HER_INFLIGHT = 4;
-template <typename E, int TASK, int VB>
+constexpr int HER_INFLIGHT = 4;      // default; PG_HER_INFLIGHT=1|2|4|8 selects another instantiation (A/B)
+template <typename E, int TASK, int VB, int HT = HER_INFLIGHT>
 __global__ void __launch_bounds__(256) her_relabel_kernel(const E* __restrict__ next_ag, const E* __restrict__ dg, const long long* __restrict__ src,
                                                           const long long* __restrict__ goal_src, E* __restrict__ dg_out, E* __restrict__ ag_out,
                                                           float* __restrict__ reward, long long m, long long pitch, int reward_type, double threshold) {
-    constexpr int G = task_goal_dim(TASK), HT = HER_INFLIGHT;
+    constexpr int G = task_goal_dim(TASK);
     using RL = RowLoad<E, G, VB>;
     const E thr = (E)threshold;
     const long long stride = (long long)gridDim.x * blockDim.x;
