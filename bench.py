@@ -370,6 +370,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (kt.get("dram_bytes_per_launch") * kt.get("step_kernel_launches_per_step")) if kt else None,
                          "kernel": "step_kernel", "launches_per_step": kt.get("launches_per_step") if kt else None, "traffic_source": kt.get("source") if kt else None,
+                         "ncu": {k: kt.get(k) for k in ("fma_pipe_pct", "issue_active_pct", "threads_per_instruction", "warps_active_pct", "kernel_us_under_ncu")} if kt else None,
                          "bytes_per_env_step": bps, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "latency/issue-bound kernel (~1 MFLOP of serial dynamics per env-step): the HBM fraction is structurally tiny, see DESIGN.md"},
             "also": also,

@@ -39,7 +39,11 @@ def main():
         rd = float(r["dram__bytes_read.sum"][0]) * UNIT[r["dram__bytes_read.sum"][1]]
         wr = float(r["dram__bytes_write.sum"][0]) * UNIT[r["dram__bytes_write.sum"][1]]
         t = float(r["gpu__time_duration.sum"][0]) * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}[r["gpu__time_duration.sum"][1]]
-        table[key] = {"dram_bytes_per_launch": rd + wr, "step_kernel_launches_per_step": int(launches), "launches_per_step": desc, "kernel_us_under_ncu": t,
+        def pct(name):
+            return float(r[name][0]) if name in r else None
+        table[key] = {"fma_pipe_pct": pct("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"), "issue_active_pct": pct("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                      "threads_per_instruction": pct("smsp__thread_inst_executed_per_inst_executed.ratio"), "warps_active_pct": pct("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                      "dram_bytes_per_launch": rd + wr, "step_kernel_launches_per_step": int(launches), "launches_per_step": desc, "kernel_us_under_ncu": t,
                       "grid": r["launch__grid_size"][0], "kernel": r["Kernel Name"][0], "source": os.path.relpath(os.path.abspath(path), ROOT)}
     json.dump(table, open(dst, "w"), indent=1, sort_keys=True)
     print(json.dumps(table, indent=1, sort_keys=True))
