@@ -38,6 +38,8 @@ def test_scripted_success_rate_matches_oracle(task, n, min_rate):
     print(f"scripted {task}: gpu {gpu.mean():.4f} vs oracle {ref.mean():.4f} over the same {n} episodes; per-episode agreement {agree:.4f}")
     assert gpu.mean() > min_rate, gpu.mean()                  # the script actually solves the task (grasp / push / stack work)
     assert abs(gpu.mean() - ref.mean()) <= 0.01, (gpu.mean(), ref.mean())
-    # per-episode agreement: the grasp and the push are robust (measured 1.0000 / 0.990); a stacked cube released a few mm off-centre
-    # rests on two diagonal contact points and whether it topples is decided at fp32 resolution (measured 0.87) -- the RATE still agrees
+    # per-episode agreement: the grasp and the push are robust (measured 1.0000 / 0.990); Stack's script carries the second cube in a grasp
+    # that pivots about the two fingertip contact lines and sets it down while still moving, so whether the cube ends on top or beside is
+    # decided at fp32 resolution in many episodes (measured 0.87; the oracle ends with the cube on top in 17 % of the episodes, the 70 %
+    # "success" is the task's loose 0.1 threshold on the 6-D goal distance) -- the RATE still agrees
     assert agree >= {"pick_and_place": 0.97, "push": 0.95, "stack": 0.8}[task], agree
